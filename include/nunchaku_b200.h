@@ -1,0 +1,159 @@
+/*
+ * nunchaku_b200 -- C ABI of the B200-native SVDQuant W4A4 fused linear.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device
+ * pointers, sizes and a CUDA stream handle -- no torch / C++ types -- and returns 0 on
+ * success or a negative nb200_status; nb200_last_error() returns a thread-local message.
+ * All launches are asynchronous on `stream` (the reference launches on torch's current
+ * stream: src/interop/torch.cpp:84-91, src/common.h:60-67).
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *
+ *   nb200_quantize_w4a4_act_fuse_lora  <->  nunchaku::kernels::quantize_w4a4_act_fuse_lora
+ *        src/kernels/zgemm/zgemm.h:39-46, gemm_w4a4.cu:113-125,
+ *        gemm_w4a4_launch_impl.cuh:451-521, kernel gemm_w4a4.cuh:1097-1184
+ *   nb200_gemm_w4a4                    <->  nunchaku::kernels::gemm_w4a4
+ *        src/kernels/zgemm/zgemm.h:8-36, gemm_w4a4.cu:34-105,
+ *        gemm_w4a4_launch_impl.cuh:7-424, kernels gemm_w4a4.cuh:358-405,1046-1095
+ *   nb200_repack_*                     <->  (no reference twin) one-time, at parameter-load
+ *        time, conversion of the reference's mma.sync-fragment-ordered tensors
+ *        (nunchaku/lora/flux/packer.py:187-437; GEMM_W4A4::loadParam src/Linear.cpp:124-154)
+ *        into the TMA / tcgen05 friendly layouts below.  Pure permutations (+ dtype
+ *        widening for bias/scales, + folding 1/(alpha*wcscale) into lora_up).
+ *
+ * Layouts ("B200 layouts", all row-major, K innermost):
+ *
+ *   act / qweight  INT4 : u8 [rows, K/2].  Each aligned group of 8 consecutive k is one
+ *                         little-endian u32; nibble p (p<4) holds element 2p, nibble p+4
+ *                         holds element 2p+1.  Signed values are stored offset-binary
+ *                         (q + 8); unsigned activations (act_unsigned) are stored as is.
+ *                  NVFP4: u8 [rows, K/2], e2m1 codes, low nibble = even k.
+ *   ascales/wscales INT4 : hT [K/64, rows]            (group-major, rows contiguous)
+ *                  NVFP4: u8 (ue4m3) tiles [rows/128][K/64][32][16]: the byte for
+ *                         (row r, 16-group c of a 64-wide k block) sits at
+ *                         (r%32)*16 + ((r%128)/32)*4 + c  -- the tcgen05.cp 32x128b layout.
+ *   lora_act            : f32 [Mp, R] row-major.
+ *   lora_up  (B200)     : hT, blocks [Rp/32][N/8][4][8][8]  (UMMA no-swizzle K-major core
+ *                         matrices; Rp = R rounded up to 32, zero padded), pre-multiplied by
+ *                         1/cscale[n].
+ *   lora_down (B200)    : hT, [K/16][Rp/8][32 lanes][4]  mma.sync B-fragment order used by
+ *                         the quantize kernel (see csrc/quantize.cu).
+ *   bias, cscale        : f32 [N]    (cscale = alpha * wcscales, 1 when absent)
+ *   smooth              : hT [K] in natural order.
+ */
+#ifndef NUNCHAKU_B200_H_
+#define NUNCHAKU_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_ABI_VERSION 1
+
+typedef enum nb200_status {
+    NB200_OK = 0,
+    NB200_ERR_INVALID_ARGUMENT = -1, /* shape / alignment / null-pointer precondition  */
+    NB200_ERR_UNSUPPORTED = -2,      /* valid in the reference, not built here yet      */
+    NB200_ERR_CUDA = -3,             /* a CUDA runtime / driver call failed             */
+    NB200_ERR_ARCH = -4              /* device is not sm_100                            */
+} nb200_status;
+
+typedef enum nb200_dtype { NB200_FP16 = 0, NB200_BF16 = 1 } nb200_dtype;
+
+/* mid-epilogue activation (reference: EpilogueNop / EpilogueSilu / EpilogueGelu) */
+typedef enum nb200_act { NB200_ACT_NONE = 0, NB200_ACT_SILU = 1, NB200_ACT_GELU = 2 } nb200_act;
+
+#define NB200_MAX_LORA_SCALES 64 /* MAX_RANK / 16, src/kernels/zgemm/lora.cuh:22,41 */
+
+/* ---- introspection ------------------------------------------------------------------ */
+int nb200_abi_version(void);
+const char *nb200_last_error(void);
+/* 0 when the current device is compute capability 10.x, NB200_ERR_ARCH otherwise. */
+int nb200_check_device(void);
+
+/* ---- one-time repack of reference-layout parameters (device -> device) --------------- */
+/* qweight: reference int8 [N, K/2] (packer.py:187-239)  ->  B200 u8 [N, K/2]. */
+int nb200_repack_qweight(const void *src, void *dst, int N, int K, int fp4, void *stream);
+/* INT4 wscales: reference hT "[K/64, N]" (packer.py:241-301) -> hT [K/64, N] natural. */
+int nb200_repack_wscales_int4(const void *src, void *dst, int N, int K, void *stream);
+/* NVFP4 wscales: reference fp8 "[K/16, N]" (packer.py:303-360) -> ue4m3 tiles. */
+int nb200_repack_wscales_fp4(const void *src, void *dst, int N, int K, void *stream);
+/* bias / smooth / wcscales: reference hT [N] in pack_scale(group_size=-1) order ->
+ * natural order; out_f32 != 0 widens to float and multiplies by `mul` (cscale = alpha*wcs). */
+int nb200_repack_channel_vector(const void *src, void *dst, int N, int dtype, int out_f32, float mul, void *stream);
+/* lora_up: reference hT [N, R] (packer.py:362-398) -> B200 blocks, divided by cscale[n]
+ * (cscale may be NULL == 1).  dst holds N * Rp elements, Rp = ceil(R/32)*32. */
+int nb200_repack_lora_up(const void *src, void *dst, const float *cscale, int N, int R, int dtype, void *stream);
+/* lora_down: reference hT [K, R] -> B200 fragment order for the quantize kernel
+ * (dst holds K * Rp8 elements, Rp8 = R). */
+int nb200_repack_lora_down(const void *src, void *dst, int K, int R, int dtype, void *stream);
+
+/* ---- activation quantize + low-rank down projection ---------------------------------- */
+typedef struct nb200_quantize_args {
+    const void *input;     /* hT [M, K] row-major ([M, 2K] when fuse_glu)                 */
+    void *output;          /* u8 [Mp, K/2]                                                 */
+    void *oscales;         /* INT4: hT [K/64, Mp];  NVFP4: ue4m3 tiles, K/16*Mp bytes      */
+    const void *lora_down; /* B200 layout (nb200_repack_lora_down), R > 0                  */
+    float *lora_act_out;   /* f32 [Mp, R]; fully overwritten (reference zero-fills first)  */
+    const void *smooth;    /* hT [K] natural order, or NULL                                */
+    int M;                 /* valid rows                                                   */
+    int Mp;                /* padded rows, multiple of 256 (pad_size, ops/quantize.py:66)  */
+    int K;                 /* multiple of 128                                              */
+    int R;                 /* multiple of 16                                               */
+    int dtype;             /* nb200_dtype                                                  */
+    int fuse_glu;
+    int fp4;
+} nb200_quantize_args;
+
+int nb200_quantize_w4a4_act_fuse_lora(const nb200_quantize_args *args, void *stream);
+
+/* ---- fused W4A4 GEMM ------------------------------------------------------------------ */
+typedef struct nb200_gemm_args {
+    /* operands (B200 layouts) */
+    const void *act;       /* u8 [Mp, K/2]                                                 */
+    const void *wgt;       /* u8 [N, K/2]                                                  */
+    const void *ascales;
+    const void *wscales;
+    /* epilogue inputs */
+    const float *bias;     /* f32 [N] or NULL                                              */
+    const float *cscale;   /* f32 [N] or NULL (== alpha * wcscales)                        */
+    const float *lora_act_in; /* f32 [Mp, R_up] or NULL                                    */
+    const void *lora_up;   /* B200 layout or NULL                                          */
+    /* outputs: mode is selected by which are non-NULL, as in the reference
+     * (gemm_w4a4_launch_impl.cuh:282,311,347,407)                                         */
+    void *out;             /* hT [M_out, N_out] row-major or NULL                          */
+    void *qout;            /* u8 [Mp, N/2]: next layer's quantized activations, or NULL    */
+    void *oscales;         /* scales of qout                                               */
+    const void *smooth_next;    /* hT [N] natural, required with qout                      */
+    const void *lora_down_next; /* hT B200 "UMMA-B" layout for the fused down projection   */
+    float *lora_act_out;   /* f32 [Mp, R_down]; zeroed then accumulated                    */
+    const void *norm_q;    /* hT [128]   RMSNorm weights (rotary mode)                     */
+    const void *norm_k;
+    const float *rotary_emb; /* f32, reference pack_rotemb layout [Mp, 128]                */
+    /* sizes */
+    int Mp, N, K;          /* Mp % 256 == 0, N % 128 == 0, K % 128 == 0                    */
+    int M_out, N_out;      /* rows / cols of `out` actually stored (<= Mp, N)              */
+    int R_up, R_down;
+    /* flags */
+    int dtype;             /* nb200_dtype of out / scales / lora                           */
+    int fp4;
+    int act_unsigned;      /* INT4 only: act nibbles are 0..15                             */
+    int mid_act;           /* nb200_act; GELU is implied when qout != NULL                 */
+    float lora_scales[NB200_MAX_LORA_SCALES];
+    /* tuning (0 = auto) */
+    int block_n;
+    int num_sms;
+} nb200_gemm_args;
+
+int nb200_gemm_w4a4(const nb200_gemm_args *args, void *stream);
+
+/* Number of kernels the last nb200_* call on this thread launched (bench bookkeeping). */
+int nb200_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUNCHAKU_B200_H_ */

@@ -1,0 +1,130 @@
+"""Mirror of nunchaku/ops/gemm.py:12-160 (svdq_gemm_w4a4_cuda) on B200."""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from .. import repack
+from .._C import NB200_ACT_GELU, NB200_ACT_NONE, NB200_ACT_SILU, NB200_MAX_LORA_SCALES, GemmArgs, check, lib
+from ..utils import torch_dtype_code
+
+# tuning knobs for experiments (0 = let the launcher choose)
+BLOCK_N_OVERRIDE = 0
+NUM_SMS_OVERRIDE = 0
+
+
+def svdq_gemm_w4a4_cuda(
+    act: torch.Tensor,
+    wgt: torch.Tensor,
+    out: torch.Tensor | None = None,
+    qout: torch.Tensor | None = None,
+    ascales: torch.Tensor | None = None,
+    wscales: torch.Tensor | None = None,
+    oscales: torch.Tensor | None = None,
+    poolout: torch.Tensor | None = None,
+    lora_act_in: torch.Tensor | None = None,
+    lora_up: torch.Tensor | None = None,
+    lora_down: torch.Tensor | None = None,
+    lora_act_out: torch.Tensor | None = None,
+    norm_q: torch.Tensor | None = None,
+    norm_k: torch.Tensor | None = None,
+    rotary_emb: torch.Tensor | None = None,
+    bias: torch.Tensor | None = None,
+    smooth_factor: torch.Tensor | None = None,
+    out_vk: torch.Tensor | None = None,
+    out_linearattn: torch.Tensor | None = None,
+    act_unsigned: bool = False,
+    lora_scales: list[float] | None = None,
+    fuse_silu: bool = False,
+    fp4: bool = False,
+    alpha: float | None = 1.0,
+    wcscales: torch.Tensor | None = None,
+    out_q: torch.Tensor | None = None,
+    out_k: torch.Tensor | None = None,
+    out_v: torch.Tensor | None = None,
+    attn_tokens: int = 0,
+):
+    """Fused SVDQuant W4A4 GEMM; positional/keyword compatible with the reference wrapper
+    (nunchaku/ops/gemm.py:12-160).  Results are written in place into the provided outputs.
+
+    ``act`` / ``ascales`` / ``lora_act_in`` must come from this package's quantize op (or fused
+    epilogue); ``wgt`` / ``wscales`` / ``lora_up`` / ``bias`` / ``wcscales`` are the reference's
+    packed checkpoint tensors and are repacked once on first use (nunchaku_b200.repack).
+    ``poolout`` is accepted and ignored exactly as in the reference.
+    """
+    if act is None or wgt is None or ascales is None or wscales is None:
+        raise ValueError("act, wgt, ascales and wscales are required")
+    if not act.is_cuda:
+        raise RuntimeError("nunchaku_b200 has no CPU path: act must be a CUDA tensor")
+    if out_vk is not None or out_linearattn is not None:
+        raise NotImplementedError("SANA LiteLA epilogue (out_vk/out_linearattn) is not built yet")
+    if out_q is not None or out_k is not None or out_v is not None:
+        raise NotImplementedError("PackQKV epilogue (out_q/out_k/out_v) is not built yet")
+    if qout is not None or oscales is not None or rotary_emb is not None or lora_down is not None:
+        raise NotImplementedError("fused next-layer quantize / RMSNorm+RoPE epilogues are not built yet")
+    if out is None:
+        raise ValueError("out is required")
+    if alpha is None:
+        alpha = 1.0
+    if not fp4 and float(alpha) != 1.0:
+        raise ValueError("INT4 requires alpha == 1 (gemm_w4a4_launch_impl.cuh:107)")
+
+    Mp = act.numel() // act.shape[-1]
+    K = act.shape[-1] * 2
+    N = wgt.shape[0]
+    if wgt.shape[1] * 2 != K:
+        raise ValueError("act and wgt disagree on K")
+    out2d = out.view(-1, out.shape[-1])
+    dtype = out.dtype
+
+    args = GemmArgs()
+    args.act = act.data_ptr()
+    args.wgt = repack.qweight(wgt, fp4).data_ptr()
+    args.ascales = ascales.data_ptr()
+    args.wscales = repack.wscales(wscales, N, K, fp4).data_ptr()
+    cs = None
+    if wcscales is not None or float(alpha) != 1.0:
+        if wcscales is not None:
+            cs = repack.channel_vector(wcscales, out_f32=True, mul=float(alpha))
+        else:
+            cs = _const_vector(N, float(alpha), act.device)
+    args.cscale = None if cs is None else cs.data_ptr()
+    args.bias = None if bias is None else repack.channel_vector(bias, out_f32=True).data_ptr()
+    rank = 0
+    if lora_up is not None:
+        if lora_act_in is None:
+            raise ValueError("lora_up and lora_act_in go together (launch_impl:198)")
+        rank = lora_up.shape[1]
+        if rank > 0:
+            args.lora_up = repack.lora_up(lora_up, cs).data_ptr()
+            args.lora_act_in = lora_act_in.data_ptr()
+            assert lora_act_in.shape[-1] == rank and lora_act_in.dtype == torch.float32
+    if lora_scales is None:
+        lora_scales = [1.0] * math.ceil(rank / 16)
+    for i in range(NB200_MAX_LORA_SCALES):  # absent groups get 0 (launch_impl:220-225)
+        args.lora_scales[i] = float(lora_scales[i]) if i < len(lora_scales) else 0.0
+    args.out = out2d.data_ptr()
+    args.Mp, args.N, args.K = Mp, N, K
+    args.M_out, args.N_out = out2d.shape[0], out2d.shape[1]
+    args.R_up, args.R_down = rank, 0
+    args.dtype = torch_dtype_code(dtype)
+    args.fp4 = int(fp4)
+    args.act_unsigned = int(act_unsigned)
+    args.mid_act = NB200_ACT_SILU if fuse_silu else NB200_ACT_NONE
+    args.block_n = BLOCK_N_OVERRIDE
+    args.num_sms = NUM_SMS_OVERRIDE
+    check(lib.nb200_gemm_w4a4(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "gemm_w4a4")
+
+
+_const_cache: dict[tuple, torch.Tensor] = {}
+
+
+def _const_vector(n: int, value: float, device) -> torch.Tensor:
+    key = (n, value, str(device))
+    t = _const_cache.get(key)
+    if t is None:
+        t = torch.full((n,), value, dtype=torch.float32, device=device)
+        _const_cache[key] = t
+    return t

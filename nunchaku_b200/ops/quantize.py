@@ -1,0 +1,76 @@
+"""Mirror of nunchaku/ops/quantize.py:10-80 (svdq_quantize_w4a4_act_fuse_lora_cuda) on B200."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .. import repack
+from .._C import QuantizeArgs, check, lib
+from ..utils import ceil_divide, torch_dtype_code
+
+
+def svdq_quantize_w4a4_act_fuse_lora_cuda(
+    input: torch.Tensor,
+    output: torch.Tensor | None = None,
+    oscales: torch.Tensor | None = None,
+    lora_down: torch.Tensor | None = None,
+    lora_act_out: torch.Tensor | None = None,
+    smooth: torch.Tensor | None = None,
+    fuse_glu: bool = False,
+    fp4: bool = False,
+    pad_size: int = 256,
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Quantize activations to 4 bit and compute the low-rank down projection.
+
+    Same arguments, shapes, dtypes and return value as the reference wrapper
+    (nunchaku/ops/quantize.py:10-80).  ``lora_down`` and ``smooth`` arrive in the reference's
+    packed checkpoint layout; the three outputs are produced by and only meaningful to this
+    package's GEMM (their *internal* element order is the B200 inter-op layout, exactly as the
+    reference's outputs are in its own fragment order)::
+
+        output        (M_pad, K // 2)   uint8
+        oscales       (K // G, M_pad)   input dtype (INT4, G=64) | float8_e4m3fn (NVFP4, G=16)
+        lora_act_out  (M_pad, R)        float32
+    """
+    if input.dim() != 2:
+        raise ValueError("input must be 2-D (M, K)")
+    if lora_down is None:
+        raise ValueError("lora_down is required (the reference dereferences it unconditionally)")
+    if not input.is_cuda:
+        raise RuntimeError("nunchaku_b200 has no CPU path: input must be a CUDA tensor")
+    input = input.contiguous()
+    batch_size, channels = input.shape
+    if fuse_glu:
+        channels //= 2
+    rank = lora_down.shape[1]
+    if pad_size % 256 != 0:
+        raise ValueError("pad_size must be a multiple of 256 (kernel tile, launch_impl:462-463)")
+    batch_size_pad = ceil_divide(batch_size, pad_size) * pad_size
+    if output is None:
+        output = torch.empty(batch_size_pad, channels // 2, dtype=torch.uint8, device=input.device)
+    if oscales is None:
+        if fp4:
+            assert channels % 16 == 0
+            oscales = torch.empty(channels // 16, batch_size_pad, dtype=torch.float8_e4m3fn, device=input.device)
+        else:
+            assert channels % 64 == 0
+            oscales = torch.empty(channels // 64, batch_size_pad, dtype=input.dtype, device=input.device)
+    if lora_act_out is None:
+        lora_act_out = torch.empty(batch_size_pad, rank, dtype=torch.float32, device=input.device)
+    assert output.shape[0] == batch_size_pad and output.is_contiguous()
+    assert lora_act_out.shape == (batch_size_pad, rank) and lora_act_out.dtype == torch.float32
+
+    args = QuantizeArgs()
+    args.input = input.data_ptr()
+    args.output = output.data_ptr()
+    args.oscales = oscales.data_ptr()
+    args.lora_down = repack.lora_down(lora_down).data_ptr()
+    args.lora_act_out = lora_act_out.data_ptr()
+    args.smooth = None if smooth is None else repack.channel_vector(smooth, out_f32=False).data_ptr()
+    args.M, args.Mp, args.K, args.R = batch_size, batch_size_pad, channels, rank
+    args.dtype = torch_dtype_code(input.dtype)
+    args.fuse_glu, args.fp4 = int(fuse_glu), int(fp4)
+    check(lib.nb200_quantize_w4a4_act_fuse_lora(ctypes.byref(args), torch.cuda.current_stream().cuda_stream),
+          "quantize_w4a4_act_fuse_lora")
+    return output, oscales, lora_act_out

@@ -1,0 +1,195 @@
+"""GPU parity: gemm_w4a4 (tcgen05 kernel, through the C ABI) vs the CPU oracle and, at
+BASELINE.json's full sizes, vs an fp32 torch evaluation of the same quantised operands on the GPU.
+
+Tolerances (north_star: "within 1e-2 relative on the GEMM output"):
+  * vs oracle mode="exact" (fp64 on identical quantised operands):  rel-Frobenius <= 2e-3
+    (our kernel: exact products, fp32 accumulation, one hT rounding of the INT4 operands);
+  * vs oracle mode="ref" (emulates the reference kernel's 16-bit accumulation chain):
+    rel-Frobenius <= 1e-2 -- the gate the reference comparison is specified with;
+  * and ours must be at least as close to exact as the reference emulation is (A.6).
+"""
+import pytest
+import torch
+
+import b200_layouts as L
+from gpu_util import diag, ref_layout_params
+from oracle import svdq as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(layer, qa, params, M, *, block_n=0, fuse_silu=False, act_unsigned=False, lora_scales=None, with_bias=True,
+          with_lora=True):
+    from nunchaku_b200.ops import gemm as G
+
+    hT = layer.hT
+    Mp, K = qa.q.shape
+    N = layer.qw.shape[0]
+    if layer.fp4:
+        act = L.pack_fp4(qa.q).cuda()
+        asc = L.pack_sf_tiles(qa.scales.t().contiguous()).view(torch.float8_e4m3fn).view(K // 16, Mp).cuda()
+    else:
+        act = L.pack_int4(qa.q, signed=not act_unsigned).cuda()
+        asc = qa.scales.cuda()
+    out = torch.full((M, N), float("nan"), dtype=hT, device="cuda")
+    G.BLOCK_N_OVERRIDE = block_n
+    try:
+        G.svdq_gemm_w4a4_cuda(
+            act=act, wgt=params["qweight"], out=out, ascales=asc, wscales=params["wscales"],
+            lora_act_in=qa.lora_act.cuda() if with_lora else None, lora_up=params["proj_up"] if with_lora else None,
+            bias=params["bias"] if with_bias else None, fp4=layer.fp4, alpha=layer.alpha, wcscales=params["wcscales"],
+            act_unsigned=act_unsigned, fuse_silu=fuse_silu, lora_scales=lora_scales)
+        torch.cuda.synchronize()
+    finally:
+        G.BLOCK_N_OVERRIDE = 0
+    return out
+
+
+def _oracle(layer, qa, M, mode, **kw):
+    return O.gemm_w4a4(qa=qa.q, ascales=qa.scales, qw=layer.qw, wscales=layer.wscales, hT=layer.hT, M=M,
+                       bias=kw.get("bias", layer.bias), lora_act=qa.lora_act if kw.get("with_lora", True) else None,
+                       lora_up=layer.lora_up if kw.get("with_lora", True) else None, fp4=layer.fp4, alpha=layer.alpha,
+                       wcscales=layer.wcscales, act=kw.get("act", "none"), lora_scales=kw.get("lora_scales"), mode=mode).out
+
+
+def _assert_parity(out, y_exact, y_ref, hT, name):
+    e_exact = O.rel_fro(out.cpu(), y_exact)
+    e_ref = O.rel_fro(out.cpu(), y_ref)
+    ref_noise = O.rel_fro(y_ref, y_exact)
+    msg = f"{name}: ours-vs-exact {e_exact:.3e} ours-vs-ref {e_ref:.3e} ref-vs-exact {ref_noise:.3e}\n" + diag(name, out, y_exact)
+    assert not torch.isnan(out).any(), msg
+    assert e_exact <= 2e-3, msg
+    assert e_ref <= 1e-2, msg
+    assert e_exact <= ref_noise + 2e-3, msg
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("fp4", [False, True])
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+def test_gemm_small(fp4, hT, block_n):
+    N, K, R, M = 256, 384, 32, 200       # K not a multiple of 256: exercises the FP4 k tail
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=11)
+    x = O.make_activations(M, K, hT, seed=12, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=fp4)
+    params = ref_layout_params(layer)
+    out = _gemm(layer, qa, params, M, block_n=block_n)
+    _assert_parity(out, _oracle(layer, qa, M, "exact"), _oracle(layer, qa, M, "ref"), hT, f"small fp4={fp4} bn={block_n}")
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+def test_gemm_main_only_then_pieces(fp4):
+    """Peel the epilogue: main GEMM alone, + bias, + low-rank -- localises a failure."""
+    hT = torch.bfloat16
+    N, K, R, M = 256, 512, 32, 256
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=21, with_wcscales=False)
+    layer.alpha = 1.0 if not fp4 else layer.alpha
+    x = O.make_activations(M, K, hT, seed=22, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=fp4)
+    params = ref_layout_params(layer)
+    for with_bias, with_lora in [(False, False), (True, False), (True, True)]:
+        out = _gemm(layer, qa, params, M, with_bias=with_bias, with_lora=with_lora)
+        kw = dict(bias=layer.bias if with_bias else None, with_lora=with_lora)
+        _assert_parity(out, _oracle(layer, qa, M, "exact", **kw), _oracle(layer, qa, M, "ref", **kw), hT,
+                       f"pieces fp4={fp4} bias={with_bias} lora={with_lora}")
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+def test_gemm_rank_variants_and_lora_scales(fp4):
+    hT = torch.bfloat16
+    N, K, M = 256, 256, 256
+    for R, scales in [(16, None), (48, [0.5, 2.0, 1.0]), (64, [1.0, 0.0, 1.0, -1.0])]:
+        layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=31 + R)
+        x = O.make_activations(M, K, hT, seed=32, smooth=layer.smooth)
+        qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=fp4)
+        out = _gemm(layer, qa, ref_layout_params(layer), M, lora_scales=scales)
+        _assert_parity(out, _oracle(layer, qa, M, "exact", lora_scales=scales),
+                       _oracle(layer, qa, M, "ref", lora_scales=scales), hT, f"rank {R} fp4={fp4}")
+
+
+def test_gemm_int4_unsigned_act_and_silu():
+    hT = torch.bfloat16
+    N, K, R, M = 256, 256, 32, 256
+    layer = O.make_synthetic_layer(N, K, R, fp4=False, hT=hT, seed=41)
+    g = torch.Generator().manual_seed(42)
+    qa = O.quantize_w4a4_act_fuse_lora(O.make_activations(M, K, hT, seed=43, smooth=layer.smooth), layer.smooth,
+                                       layer.lora_down)
+    qa.q = torch.randint(0, 16, qa.q.shape, generator=g, dtype=torch.int8)     # as produced by the fused GELU epilogue
+    params = ref_layout_params(layer)
+    out = _gemm(layer, qa, params, M, act_unsigned=True)
+    _assert_parity(out, _oracle(layer, qa, M, "exact"), _oracle(layer, qa, M, "ref"), hT, "unsigned act")
+    qa2 = O.quantize_w4a4_act_fuse_lora(O.make_activations(M, K, hT, seed=44, smooth=layer.smooth), layer.smooth,
+                                        layer.lora_down)
+    out2 = _gemm(layer, qa2, params, M, fuse_silu=True)
+    _assert_parity(out2, _oracle(layer, qa2, M, "exact", act="silu"), _oracle(layer, qa2, M, "ref", act="silu"), hT, "silu")
+
+
+@pytest.mark.parametrize("precision", ["int4", "nvfp4"])
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+def test_linear_module_3072(precision, hT):
+    """BASELINE.json config 1: single SVDQuant Linear 3072x3072 rank 32 vs the CPU oracle,
+    through SVDQW4A4Linear.forward (quantize kernel + GEMM kernel)."""
+    from gpu_util import ref_layout_params
+    from nunchaku_b200.models.linear import SVDQW4A4Linear
+
+    fp4 = precision == "nvfp4"
+    N = K = 3072
+    R, M = 32, 300
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=0)
+    x = O.make_activations(M, K, hT, seed=1, smooth=layer.smooth)
+    p = ref_layout_params(layer)
+    mod = SVDQW4A4Linear(K, N, rank=R, bias=True, precision=precision, torch_dtype=hT, device="cuda")
+    sd = {"qweight": p["qweight"], "wscales": p["wscales"], "bias": p["bias"], "smooth_factor": p["smooth"],
+          "smooth_factor_orig": p["smooth"], "proj_down": p["proj_down"], "proj_up": p["proj_up"]}
+    if fp4:
+        sd["wcscales"] = p["wcscales"]
+        mod.wtscale = layer.alpha
+    mod.load_state_dict(sd)
+    y = mod(x.cuda().view(1, M, K)).view(M, N)
+    torch.cuda.synchronize()
+    y_ref = O.svdq_linear_forward(layer, x, mode="ref")
+    y_ex = O.svdq_linear_forward(layer, x, mode="exact")
+    # the device quantiser may flip a few codes by one step (approx reciprocal), so the end-to-end
+    # gate is the north_star one: 1e-2 relative against the reference-emulating oracle
+    e_ref, e_ex = O.rel_fro(y.cpu(), y_ref), O.rel_fro(y.cpu(), y_ex)
+    msg = f"linear {precision} {hT}: vs ref {e_ref:.3e} vs exact {e_ex:.3e} ref-vs-exact {O.rel_fro(y_ref, y_ex):.3e}\n" + diag("linear", y, y_ex)
+    assert e_ref <= 1e-2 and e_ex <= 5e-3, msg
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+def test_gemm_full_size_vs_fp32_on_gpu(fp4):
+    """M=4352 (FLUX.1-schnell single stream), 3072x3072 r=32: too big for the CPU oracle in
+    seconds, so evaluate the SAME quantised operands in fp32 with torch on the GPU
+    (size-independent property: the kernel is linear in the dequantised operands)."""
+    hT = torch.bfloat16
+    N = K = 3072
+    R, M = 32, 4352
+    Mp = 4352
+    g = torch.Generator().manual_seed(5)
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=2)
+    params = ref_layout_params(layer)
+    dev = "cuda"
+    if fp4:
+        qa_q = torch.randint(0, 16, (Mp, K), generator=g, dtype=torch.int8)
+        qa_s = torch.randint(40, 72, (K // 16, Mp), generator=g, dtype=torch.uint8)    # e4m3 ~ [0.06, 1]
+        a = (O.e2m1_decode(qa_q.to(dev)).view(Mp, K // 16, 16) * O.e4m3_decode(qa_s.to(dev)).t().unsqueeze(-1)).view(Mp, K).float()
+        w = (O.e2m1_decode(layer.qw.to(dev)).view(N, K // 16, 16) * O.e4m3_decode(layer.wscales.to(dev)).unsqueeze(-1)).view(N, K).float()
+    else:
+        qa_q = torch.randint(-8, 8, (Mp, K), generator=g, dtype=torch.int8)
+        qa_s = (torch.rand(K // 64, Mp, generator=g) * 0.2 + 0.05).to(hT)
+        a = (qa_q.to(dev).float().view(Mp, K // 64, 64) * qa_s.to(dev).float().t().unsqueeze(-1)).view(Mp, K)
+        w = (layer.qw.to(dev).float().view(N, K // 64, 64) * layer.wscales.to(dev).float().unsqueeze(-1)).view(N, K)
+    la = torch.randn(Mp, R, generator=g)
+    qa = O.QuantizedAct(q=qa_q, scales=qa_s, lora_act=la, M=M)
+    out = _gemm(layer, qa, params, M)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        y = (a.double() @ w.double().t()) * layer.alpha
+        if layer.wcscales is not None:
+            y = y * layer.wcscales.to(dev).double().view(1, N)
+        y = y + layer.bias.to(dev).double().view(1, N)
+        y = y + la.to(dev).to(hT).double() @ layer.lora_up.to(dev).double().t()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    e = O.rel_fro(out.cpu(), y.cpu()[:M])
+    assert e <= 3e-3, f"full size fp4={fp4}: rel_fro {e:.3e}\n" + diag("full", out, y[:M])
