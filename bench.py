@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- FLUX.1-schnell 1024x1024 4-step, SVDQuant W4A4 + low-rank linear stack on B200.
+
+A "step" is one denoising step's worth of the hot path: every SVDQuant linear of the
+FLUX.1-schnell transformer (19 joint blocks x {qkv, out, fc1, fc2} for the 4096-token image
+stream and the 256-token text stream, 38 single blocks x {qkv, out, fc1, fc2} on 4352 tokens)
+= 304 fused W4A4 GEMM launches + their activation-quantize launches, at the model's exact shapes,
+rank 32, synthetic random-init 4-bit weights (no checkpoints offline) and synthetic activations.
+Attention / AdaLN / elementwise glue are outside the hot path and not run.
+An image is 4 steps.  value = images/s of this stack, whole job over all ranks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision int4|nvfp4] [--impl reference]
+
+JSON keys follow the driver contract (+ roofline, cpu_baseline, e2e, clocks, gpu_launches).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIM, MLP, RANK = 3072, 12288, 32
+IMG_TOKENS, TXT_TOKENS = 4096, 256
+N_JOINT, N_SINGLE = 19, 38
+STEPS_PER_IMAGE = 4
+
+# (name, K, N, activation)
+BLOCK_LINEARS = [("qkv", DIM, 3 * DIM, "none"), ("out", DIM, DIM, "none"), ("fc1", DIM, MLP, "gelu"), ("fc2", MLP, DIM, "none")]
+
+
+def layer_list():
+    """[(tag, M, K, N, act)] for one denoising step, in execution order."""
+    layers = []
+    for b in range(N_JOINT):
+        for stream, M in (("img", IMG_TOKENS), ("txt", TXT_TOKENS)):
+            for name, K, N, act in BLOCK_LINEARS:
+                layers.append((f"joint{b}.{stream}.{name}", M, K, N, act))
+    for b in range(N_SINGLE):
+        for name, K, N, act in BLOCK_LINEARS:
+            layers.append((f"single{b}.{name}", IMG_TOKENS + TXT_TOKENS, K, N, act))
+    return layers
+
+
+def step_flops():
+    f_main = f_lr = 0
+    for _, M, K, N, _ in layer_list():
+        f_main += 2 * M * K * N
+        f_lr += 2 * M * RANK * (K + N)
+    return f_main, f_lr
+
+
+def gemm_bytes(M, K, N, R, fp4):
+    G, s = (16, 1) if fp4 else (64, 2)
+    Mp = (M + 255) // 256 * 256
+    return Mp * K // 2 + (K // G) * Mp * s + N * K // 2 + (K // G) * N * s + 4 * Mp * R + 2 * N * R + 4 * N + 2 * M * N
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for i, n in enumerate(names):
+                if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic FLUX.1-schnell linear stack on the GPU (reference-layout random parameters)
+# --------------------------------------------------------------------------------------------
+def build_stack(torch, precision: str, dtype, device):
+    from nunchaku_b200.models.linear import SVDQW4A4Linear
+
+    fp4 = precision == "nvfp4"
+    g = torch.Generator(device=device).manual_seed(1234)
+    mods = []
+    for tag, M, K, N, act in layer_list():
+        m = SVDQW4A4Linear(K, N, rank=RANK, bias=True, precision=precision, torch_dtype=dtype, device=device)
+        with torch.no_grad():
+            # the packed layouts are permutations: random bytes in the reference layout ARE random weights
+            m.qweight.copy_(torch.randint(-128, 128, m.qweight.shape, generator=g, device=device, dtype=torch.int8))
+            if fp4:
+                # ue4m3 codes 0x30..0x37 = 0.5 .. 0.9375
+                m.wscales.copy_(torch.randint(0x30, 0x38, m.wscales.shape, generator=g, device=device, dtype=torch.uint8).view(torch.float8_e4m3fn))
+                m.wtscale = 1.0 / (2.6 * 0.72 * K ** 0.5)
+                m.wcscales.copy_((1.0 + 0.05 * torch.randn(N, generator=g, device=device)).to(dtype))
+            else:
+                m.wscales.copy_(((0.75 + 0.5 * torch.rand(m.wscales.shape, generator=g, device=device)) / (4.6 * K ** 0.5)).to(dtype))
+            m.bias.copy_((0.1 * torch.randn(N, generator=g, device=device)).to(dtype))
+            m.smooth_factor.copy_((0.75 + 0.5 * torch.rand(K, generator=g, device=device)).to(dtype))
+            m.proj_down.copy_((torch.randn(K, RANK, generator=g, device=device) / K ** 0.5).to(dtype))
+            m.proj_up.copy_((0.1 * torch.randn(N, RANK, generator=g, device=device) / RANK ** 0.5).to(dtype))
+        mods.append((tag, M, K, N, act, m))
+    return mods
+
+
+class StackRunner:
+    """Runs the 304 linears of one step through the public ops (quantize + GEMM)."""
+
+    def __init__(self, torch, mods, dtype, device):
+        from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
+        from nunchaku_b200.ops.quantize import svdq_quantize_w4a4_act_fuse_lora_cuda
+
+        self.torch, self.mods = torch, mods
+        self.gemm, self.quant = svdq_gemm_w4a4_cuda, svdq_quantize_w4a4_act_fuse_lora_cuda
+        g = torch.Generator(device=device).manual_seed(99)
+        # fixed, well-conditioned inputs per (M, K); outputs per (M, N); quantize scratch per (M, K)
+        self.x, self.y, self.q = {}, {}, {}
+        for _, M, K, N, act, m in mods:
+            if (M, K) not in self.x:
+                x = torch.randn(M, K, generator=g, device=device)
+                if K == MLP:
+                    x = torch.nn.functional.gelu(x, approximate="tanh")
+                self.x[(M, K)] = x.to(dtype)
+                Mp = (M + 255) // 256 * 256
+                fp4 = m.precision == "nvfp4"
+                self.q[(M, K)] = (
+                    torch.empty(Mp, K // 2, dtype=torch.uint8, device=device),
+                    torch.empty(K // 16, Mp, dtype=torch.float8_e4m3fn, device=device) if fp4
+                    else torch.empty(K // 64, Mp, dtype=dtype, device=device),
+                    torch.empty(Mp, RANK, dtype=torch.float32, device=device),
+                )
+            if (M, N) not in self.y:
+                self.y[(M, N)] = torch.empty(M, N, dtype=dtype, device=device)
+        self.gemm_events = None
+
+    def set_inputs(self, img, txt):
+        """e2e: refresh the step's inputs (the image/text stream activations)."""
+        self.x[(IMG_TOKENS, DIM)].copy_(img, non_blocking=True)
+        self.x[(TXT_TOKENS, DIM)].copy_(txt, non_blocking=True)
+
+    def step(self, record_gemm_events=False):
+        torch = self.torch
+        ev = [] if record_gemm_events else None
+        for _, M, K, N, act, m in self.mods:
+            q, s, la = self.q[(M, K)]
+            fp4 = m.precision == "nvfp4"
+            self.quant(self.x[(M, K)], output=q, oscales=s, lora_down=m.proj_down, lora_act_out=la,
+                       smooth=m.smooth_factor, fp4=fp4)
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            self.gemm(act=q, wgt=m.qweight, out=self.y[(M, N)], ascales=s, wscales=m.wscales, lora_act_in=la,
+                      lora_up=m.proj_up, bias=m.bias, fp4=fp4, alpha=m.wtscale, wcscales=m.wcscales,
+                      fuse_silu=False)
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1, 2 * M * K * N + 2 * M * RANK * N))
+        self.gemm_events = ev
+        return self.y[(IMG_TOKENS + TXT_TOKENS, DIM)]
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle's reference-emulating mode on a bounded sample of the same workload
+# --------------------------------------------------------------------------------------------
+def cpu_sample(torch, precision: str, reps: int = 1):
+    """One 3072x3072 r=32 SVDQuant linear, M=256 (the text-stream shape; BASELINE config 1) through
+    the CPU oracle in reference-emulating mode.  Returns (seconds per rep, flops per rep)."""
+    from oracle import svdq as O
+
+    fp4 = precision == "nvfp4"
+    hT = torch.bfloat16
+    layer = O.make_synthetic_layer(DIM, DIM, RANK, fp4=fp4, hT=hT, seed=0)
+    x = O.make_activations(TXT_TOKENS, DIM, hT, seed=1, smooth=layer.smooth)
+    O.svdq_linear_forward(layer, x, mode="ref")  # warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.svdq_linear_forward(layer, x, mode="ref")
+    dt = (time.perf_counter() - t0) / reps
+    flops = 2 * TXT_TOKENS * DIM * DIM + 2 * TXT_TOKENS * RANK * (DIM + DIM)
+    return dt, flops
+
+
+def run_reference_arm(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    torch.set_num_threads(os.cpu_count() or 1)
+    f_main, f_lr = step_flops()
+    flops_per_image = (f_main + f_lr) * STEPS_PER_IMAGE
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, fl = cpu_sample(torch, args.precision, reps=1)
+        if i >= args.warmup:
+            times.append(dt)
+    dt = sum(times) / len(times)
+    cpu_flops_s = fl / dt
+    value = cpu_flops_s / flops_per_image
+    sample = f"1 SVDQuant linear 3072x3072 r32 M=256 ({args.precision}), oracle reference-emulating mode, torch CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int4" if args.precision == "int4" else "nvfp4",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference has no CPU implementation of this path (SURVEY F6); this is the CPU oracle (port); value extrapolates the sample's FLOP rate to one image's hot-path FLOPs",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+METRIC = "FLUX.1-schnell 1024px 4-step images/sec (SVDQuant W4A4+LR linear stack)"
+
+
+def workload_config(args):
+    return {"workload": "FLUX.1-schnell 1024x1024 4-step bs=1: 304 SVDQuant linears/step (19 joint x (img 4096 + txt 256 tokens) + 38 single x 4352 tokens), dim 3072, mlp 12288, rank 32",
+            "precision": args.precision, "parallelism": f"replica x{args.gpus}",
+            "l2": "inputs larger than L2 (4.3 GB of 4-bit weights streamed per step)"}
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NB200_BENCH_PRECISION", "int4"), choices=["int4", "nvfp4"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from nunchaku_b200._C import check, lib
+
+    check(lib.nb200_check_device(), "check_device")
+    dtype = torch.bfloat16
+    mods = build_stack(torch, args.precision, dtype, device)
+    runner = StackRunner(torch, mods, dtype, device)
+    n_layers = len(mods)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also triggers the one-time repack) -----------------------------------------
+    for _ in range(args.warmup):
+        runner.step()
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput: captured CUDA graph of one step ---------------------------
+    graph = None
+    if not args.no_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                runner.step()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=s):
+                    runner.step()
+            torch.cuda.current_stream().wait_stream(s)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
+            graph = None
+
+    def one_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            runner.step()
+
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            one_step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    images_per_s = world * (1.0 / STEPS_PER_IMAGE) / (ms_per_step * 1e-3)
+    f_main, f_lr = step_flops()
+
+    # ---- e2e through the public API with HOST buffers --------------------------------------------
+    img_h = torch.randn(IMG_TOKENS, DIM).to(dtype).pin_memory()
+    txt_h = torch.randn(TXT_TOKENS, DIM).to(dtype).pin_memory()
+    out_h = torch.empty(IMG_TOKENS + TXT_TOKENS, DIM, dtype=dtype).pin_memory()
+    h2d = img_h.numel() * 2 + txt_h.numel() * 2
+    d2h = out_h.numel() * 2
+    for _ in range(2):
+        runner.set_inputs(img_h, txt_h)
+        out_h.copy_(runner.step(), non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        runner.set_inputs(img_h, txt_h)
+        y = runner.step()
+        out_h.copy_(y, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_images = world * (1.0 / STEPS_PER_IMAGE) / (float(t.item()) / args.steps)
+
+    # ---- roofline of the dominant kernel (fused GEMM), CUDA events on the launch stream ------------
+    runner.step(record_gemm_events=True)
+    torch.cuda.synchronize()
+    g_ms = sum(a.elapsed_time(b) for a, b, _ in runner.gemm_events)
+    g_fl = sum(f for _, _, f in runner.gemm_events)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PF sustained"
+    mult = 4.0 if args.precision == "nvfp4" else 1.0
+    achieved = g_fl / (g_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak * mult, "unit": "TFLOP/s",
+                "frac": achieved / (bf16_peak * mult), "traffic": None,
+                "kernel": "gemm_w4a4_kernel", "launches": len(runner.gemm_events),
+                "avg_launch_us": g_ms * 1e3 / len(runner.gemm_events),
+                "peak_basis": peak_src + (" x4 (FP4 pipe = 4x the 16-bit pipe)" if mult == 4.0 else " (INT4 runs on the 16-bit pipe: tcgen05 has no INT4 kind)")}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.skip_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
+            dt, fl = cpu_sample(torch, args.precision, reps=3)
+            cpu_v = (fl / dt) / ((f_main + f_lr) * STEPS_PER_IMAGE)
+            cpu = {"value": cpu_v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"1 SVDQuant linear 3072x3072 r32 M=256 ({args.precision}), oracle reference-emulating mode, {dt:.2f} s/rep x3"}
+        line = {
+            "metric": METRIC, "value": images_per_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int4" if args.precision == "int4" else "nvfp4", "data": "synthetic",
+            "config": workload_config(args),
+            "tflops": world * (f_main + f_lr) / (ms_per_step * 1e-3) / 1e12,
+            "timing": "cuda graph replay" if graph is not None else "eager launches",
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_images, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "SVDQW4A4 ops (quantize + gemm) launched from Python per layer, pinned host in/out"},
+            "gpu_launches": args.steps * 2 * n_layers,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
