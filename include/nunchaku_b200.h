@@ -36,8 +36,9 @@
  *   lora_up  (B200)     : hT, blocks [Rp/32][N/8][4][8][8]  (UMMA no-swizzle K-major core
  *                         matrices; Rp = R rounded up to 32, zero padded), pre-multiplied by
  *                         1/cscale[n].
- *   lora_down (B200)    : hT, [K/16][Rp/8][32 lanes][4]  mma.sync B-fragment order used by
- *                         the quantize kernel (see csrc/quantize.cu).
+ *   lora_down (B200)    : hT, [K/32][Rp/8][32 lanes][8]  mma.sync B-fragment order used by
+ *                         the quantize kernel (see csrc/quantize.cu); for the fused fc1 epilogue
+ *                         the next layer's factor is plain row-major [R, K].
  *   bias, cscale        : f32 [N]    (cscale = alpha * wcscales, 1 when absent)
  *   smooth              : hT [K] in natural order.
  */
@@ -88,8 +89,11 @@ int nb200_repack_channel_vector(const void *src, void *dst, int N, int dtype, in
  * (cscale may be NULL == 1).  dst holds N * Rp elements, Rp = ceil(R/32)*32. */
 int nb200_repack_lora_up(const void *src, void *dst, const float *cscale, int N, int R, int dtype, void *stream);
 /* lora_down: reference hT [K, R] -> B200 fragment order for the quantize kernel
- * (dst holds K * Rp8 elements, Rp8 = R). */
+ * (dst holds K * Rp elements, Rp = ceil(R/32)*32). */
 int nb200_repack_lora_down(const void *src, void *dst, int K, int R, int dtype, void *stream);
+/* lora_down of the NEXT layer for the fused fc1 epilogue: reference hT [K, R] -> logical [R, K]
+ * row-major (TMA source; K here is the fc1 output width N). */
+int nb200_repack_lora_down_next(const void *src, void *dst, int K, int R, int dtype, void *stream);
 
 /* ---- activation quantize + low-rank down projection ---------------------------------- */
 typedef struct nb200_quantize_args {
@@ -128,7 +132,7 @@ typedef struct nb200_gemm_args {
     void *qout;            /* u8 [Mp, N/2]: next layer's quantized activations, or NULL    */
     void *oscales;         /* scales of qout                                               */
     const void *smooth_next;    /* hT [N] natural, required with qout                      */
-    const void *lora_down_next; /* hT B200 "UMMA-B" layout for the fused down projection   */
+    const void *lora_down_next; /* hT [R_down, N] row-major (nb200_repack_lora_down_next)      */
     float *lora_act_out;   /* f32 [Mp, R_down]; zeroed then accumulated                    */
     const void *norm_q;    /* hT [128]   RMSNorm weights (rotary mode)                     */
     const void *norm_k;

@@ -51,13 +51,26 @@ struct GemmParams {
     int num_n_blocks, num_tiles;
     int mid_act;
     int act_unsigned;
+    // EPI_QUANT: fused GELU -> low-rank down projection (next layer) -> 4-bit quantise (next layer)
+    void *out;               // non-null when the hT tile is stored too
+    uint8_t *qout;           // [Mp][N/2]
+    void *oscales_out;       // INT4 hT [N/64][Mp] | FP4 scale tiles
+    const void *smooth_next; // hT [N]
+    float *lora_act_out;     // [Mp][R_down], pre-zeroed
+    int R_down, Rdp;
+    // EPI_ROPE
+    const void *norm_q, *norm_k;  // hT [128]
+    const float *rotary;          // reference pack_rotemb layout [Mp][128]
     float lora_scales[NB200_MAX_LORA_SCALES];
 };
 
-template <bool FP4, int BN>
+enum { EPI_DEFAULT = 0, EPI_QUANT = 1, EPI_ROPE = 2 };
+constexpr int kMaxRdp = 128;  // largest fused next-layer rank (smem / TMEM budget)
+
+template <bool FP4, int BN, int EPI = EPI_DEFAULT>
 struct Cfg {
     static constexpr int kBK = FP4 ? 256 : 64;                 // k elements per pipeline stage
-    static constexpr int kStages = FP4 ? (BN == 256 ? 3 : 4) : 4;  // TMA ring depth
+    static constexpr int kStages = FP4 ? ((BN == 256 || EPI == EPI_QUANT) ? 3 : 4) : 4;  // TMA ring depth
     static constexpr int kConvStages = 2;                      // INT4: converted-tile ring depth
     static constexpr int kNumAcc = FP4 ? (BN <= 128 ? 2 : 1) : 2;
     static constexpr int kABytes = FP4 ? BM * 128 : BM * 32;   // packed A tile per stage
@@ -66,14 +79,17 @@ struct Cfg {
     static constexpr int kSfbCols = BN / 8;                     // 4 K64 blocks x BN/32 columns
     static constexpr int kTmemSfa = kNumAcc * BN;
     static constexpr int kTmemSfb = kTmemSfa + kSfaCols;
+    static constexpr int kTmemLd = FP4 ? kTmemSfb + kSfbCols : kNumAcc * BN;  // EPI_QUANT: D2 [128 x Rdp]
     static constexpr int kThreads = FP4 ? 256 : 512;
     static_assert(!FP4 || kTmemSfb + kSfbCols <= 512, "TMEM budget");
     static_assert(kNumAcc * BN <= 512, "TMEM budget");
+    static_assert(EPI != EPI_QUANT || (BN == 128 && kTmemLd + kMaxRdp <= 512), "fused quantise epilogue uses 128-wide tiles");
+    static_assert(EPI != EPI_ROPE || BN == 128, "RMSNorm+RoPE epilogue: one 128-wide head per tile");
 };
 
-template <bool FP4, int BN>
+template <bool FP4, int BN, int EPI = EPI_DEFAULT>
 struct alignas(1024) Smem {
-    using C = Cfg<FP4, BN>;
+    using C = Cfg<FP4, BN, EPI>;
     // TMA-staged packed operands
     alignas(1024) uint8_t a[C::kStages][C::kABytes];
     alignas(1024) uint8_t b[C::kStages][C::kBBytes];
@@ -88,8 +104,11 @@ struct alignas(1024) Smem {
     alignas(1024) uint8_t lora_b[BN * kLoraChunk * 2];
     // epilogue staging for TMA store: [128 rows][64 cols] hT, 128B swizzle, double buffered
     alignas(1024) uint8_t out_stage[2][BM * 128];
+    // EPI_QUANT: next layer's lora_down, per 64-column chunk a K-major 128B-swizzled [Rdp][64] tile
+    alignas(1024) uint8_t ld_b[EPI == EPI_QUANT ? (BN / 64) * kMaxRdp * 128 : 16];
     float bias[BN];
     float cscale[BN];
+    float aux[256];  // EPI_QUANT: next layer's smooth factors of this tile; EPI_ROPE: RMSNorm weights (q | k)
     uint64_t full[C::kStages];
     uint64_t empty[C::kStages];
     uint64_t cfull[C::kConvStages];
@@ -99,6 +118,10 @@ struct alignas(1024) Smem {
     uint64_t lora_b_full;
     uint64_t lora_a_full;
     uint64_t lora_empty;
+    uint64_t ld_b_full;
+    uint64_t ld_b_empty;
+    uint64_t stage_mma_done[2];
+    uint64_t d2_full;
     uint32_t tmem_base;
 };
 
@@ -148,12 +171,13 @@ __device__ __forceinline__ void convert_unit(const uint8_t *pk_tile, uint8_t *cv
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool FP4, typename hT, int BN>
-__global__ void __launch_bounds__(Cfg<FP4, BN>::kThreads, 1)
+template <bool FP4, typename hT, int BN, int EPI>
+__global__ void __launch_bounds__(Cfg<FP4, BN, EPI>::kThreads, 1)
 gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_wgt,
-                 const __grid_constant__ CUtensorMap tm_out, const GemmParams p) {
-    using C = Cfg<FP4, BN>;
-    using S = Smem<FP4, BN>;
+                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_ld,
+                 const GemmParams p) {
+    using C = Cfg<FP4, BN, EPI>;
+    using S = Smem<FP4, BN, EPI>;
     using Tr = HalfTraits<hT>;
     extern __shared__ uint8_t smem_raw[];
     S &s = *reinterpret_cast<S *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -169,6 +193,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         prefetch_tensormap(&tm_act);
         prefetch_tensormap(&tm_wgt);
         prefetch_tensormap(&tm_out);
+        if constexpr (EPI == EPI_QUANT) prefetch_tensormap(&tm_ld);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < C::kStages; i++) {
@@ -186,6 +211,11 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         mbar_init(&s.lora_b_full, 1);
         mbar_init(&s.lora_a_full, kNumEpiThreads);
         mbar_init(&s.lora_empty, 1);
+        mbar_init(&s.ld_b_full, 1);
+        mbar_init(&s.ld_b_empty, 1);
+        mbar_init(&s.stage_mma_done[0], 1);
+        mbar_init(&s.stage_mma_done[1], 1);
+        mbar_init(&s.d2_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(&s.tmem_base);
@@ -199,9 +229,20 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         if (elect_one()) {
             PipeState st;
             uint32_t lora_phase = 0;
+            uint32_t ld_phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int mb = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
                 const int m0 = mb * BM, n0 = nb * BN;
+                if constexpr (EPI == EPI_QUANT) {
+                    if (p.R_down > 0) {
+                        mbar_wait(&s.ld_b_empty, ld_phase ^ 1);
+                        mbar_expect_tx(&s.ld_b_full, (BN / 64) * p.Rdp * 128);
+#pragma unroll
+                        for (int ch = 0; ch < BN / 64; ch++)
+                            tma_load_2d(s.ld_b + ch * kMaxRdp * 128, &tm_ld, &s.ld_b_full, n0 + ch * 64, 0);
+                        ld_phase ^= 1;
+                    }
+                }
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     mbar_wait(&s.empty[st.idx], st.phase ^ 1);
                     if constexpr (FP4) {
@@ -310,6 +351,12 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         uint32_t acc_phase[2] = {0, 0};
         int it = 0;
         uint32_t store_count = 0;
+        [[maybe_unused]] uint32_t ld_phase = 0, d2_phase = 0;
+        [[maybe_unused]] uint32_t smd_phase[2] = {0, 0};
+        if constexpr (EPI == EPI_ROPE) {
+            for (int i = et; i < 256; i += kNumEpiThreads)
+                s.aux[i] = Tr::to_float(reinterpret_cast<const hT *>(i < 128 ? p.norm_q : p.norm_k)[i & 127]);
+        }
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
             const int mb = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
             const int m0 = mb * BM, n0 = nb * BN;
@@ -320,6 +367,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             for (int i = et; i < BN; i += kNumEpiThreads) {
                 s.bias[i] = p.bias != nullptr ? p.bias[n0 + i] : 0.f;
                 s.cscale[i] = p.cscale != nullptr ? p.cscale[n0 + i] : 1.f;
+                if constexpr (EPI == EPI_QUANT) s.aux[i] = Tr::to_float(reinterpret_cast<const hT *>(p.smooth_next)[n0 + i]);
             }
             named_bar_sync(1, kNumEpiThreads);
 
@@ -356,6 +404,46 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             acc_phase[acc] ^= 1;
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+
+            // ---- EPI_ROPE pass 1: per-row sum of squares over the 128-wide head (epilogues.cuh:327-341)
+            [[maybe_unused]] bool do_rope = false;
+            [[maybe_unused]] float rope_coef = 1.f;
+            [[maybe_unused]] const float *normw = s.aux;
+            [[maybe_unused]] const float *rot_row = nullptr;
+            if constexpr (EPI == EPI_ROPE) {
+                const int part = nb / (p.num_n_blocks / 3);  // 0 = Q heads, 1 = K heads, 2 = V (untouched)
+                do_rope = part < 2;
+                if (do_rope) {
+                    float sumsq = 0.f;
+#pragma unroll 1
+                    for (int c32 = 0; c32 < 4; c32++) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + c32 * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float y0 = fmaf(__uint_as_float(v[i]), s.cscale[c32 * 32 + i], s.bias[c32 * 32 + i]);
+                            const float y1 = fmaf(__uint_as_float(v[i + 1]), s.cscale[c32 * 32 + i + 1], s.bias[c32 * 32 + i + 1]);
+                            const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));  // fpsum is hT
+                            sumsq = fmaf(r.x, r.x, sumsq);
+                            sumsq = fmaf(r.y, r.y, sumsq);
+                        }
+                    }
+                    rope_coef = rsqrt_approx_ftz(sumsq / 128.f + 1e-6f);
+                    normw = s.aux + part * 128;
+                    // reference pack_rotemb order (transformer_flux.py:60-92): float index of (row m, pair pr, sin|cos)
+                    //   ((((m/16*16 + pr/4)*8 + m%8)*4 + pr%4)*2 + (m%16)/8)*2 + {0,1}
+                    const int m = m0 + row;
+                    rot_row = p.rotary + (static_cast<size_t>(m >> 4) * 16 * 8 + (m & 7)) * 16 + ((m >> 3) & 1) * 2;
+                }
+            }
+            if constexpr (EPI == EPI_QUANT) {
+                if (p.R_down > 0) {
+                    mbar_wait(&s.ld_b_full, ld_phase);
+                    ld_phase ^= 1;
+                }
+            }
+
 #pragma unroll 1
             for (int ch = 0; ch < BN / 64; ch++) {
                 uint32_t v0[32], v1[32];
@@ -368,8 +456,12 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 }
                 const int buf = store_count & 1;
                 if (et == 0) bulk_wait_group_read<1>();
+                if constexpr (EPI == EPI_QUANT) {
+                    if (p.R_down > 0) mbar_wait(&s.stage_mma_done[buf], smd_phase[buf] ^ 1);
+                }
                 named_bar_sync(2, kNumEpiThreads);
                 uint8_t *srow = s.out_stage[buf] + row * 128;
+                [[maybe_unused]] uint32_t gw[32];  // EPI_QUANT: the 64 hT values of this row/chunk
 #pragma unroll
                 for (int c8 = 0; c8 < 8; c8++) {
                     uint32_t w[4];
@@ -380,33 +472,166 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         float y1 = __uint_as_float(col + 1 < 32 ? v0[col + 1] : v1[col + 1 - 32]);
                         y0 = fmaf(y0, s.cscale[ch * 64 + col], s.bias[ch * 64 + col]);
                         y1 = fmaf(y1, s.cscale[ch * 64 + col + 1], s.bias[ch * 64 + col + 1]);
-                        if (p.mid_act != NB200_ACT_NONE) {
-                            // the reference applies the activation to the hT-rounded value
+                        if constexpr (EPI == EPI_QUANT) {
+                            // fused mode always applies GELU (launch_impl:296-308) to the hT-rounded value
                             const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));
-                            if (p.mid_act == NB200_ACT_GELU) {
-                                y0 = gelu_f32(r.x);
-                                y1 = gelu_f32(r.y);
-                            } else {
-                                y0 = silu_f32(r.x);
-                                y1 = silu_f32(r.y);
+                            y0 = gelu_f32(r.x);
+                            y1 = gelu_f32(r.y);
+                        } else if constexpr (EPI == EPI_ROPE) {
+                            if (do_rope) {
+                                const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));
+                                const int hc = ch * 64 + col;  // column inside the head; pair index hc / 2
+                                const float x0 = r.x * (rope_coef * normw[hc]);
+                                const float x1 = r.y * (rope_coef * normw[hc + 1]);
+                                const int pr = hc >> 1;
+                                const float2 sc = *reinterpret_cast<const float2 *>(rot_row + (pr >> 2) * 128 + (pr & 3) * 4);
+                                y0 = x0 * sc.y - x1 * sc.x;  // (sin, cos) = (sc.x, sc.y)  epilogues.cuh:362-367
+                                y1 = x0 * sc.x + x1 * sc.y;
+                            }
+                        } else {
+                            if (p.mid_act != NB200_ACT_NONE) {
+                                // the reference applies the activation to the hT-rounded value
+                                const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));
+                                if (p.mid_act == NB200_ACT_GELU) {
+                                    y0 = gelu_f32(r.x);
+                                    y1 = gelu_f32(r.y);
+                                } else {
+                                    y0 = silu_f32(r.x);
+                                    y1 = silu_f32(r.y);
+                                }
                             }
                         }
-                        if constexpr (!Tr::kIsBf16) {  // fp16 stores clamp (gemm_base.cuh:688-696)
+                        if constexpr (!Tr::kIsBf16 && EPI != EPI_QUANT) {  // fp16 stores clamp (gemm_base.cuh:688-696)
                             y0 = fminf(fmaxf(y0, -65504.f), 65504.f);
                             y1 = fminf(fmaxf(y1, -65504.f), 65504.f);
                         }
                         typename Tr::T2 h = Tr::from_float2(make_float2(y0, y1));
                         w[i] = *reinterpret_cast<uint32_t *>(&h);
+                        if constexpr (EPI == EPI_QUANT) gw[c8 * 4 + i] = w[i];
                     }
                     *reinterpret_cast<uint4 *>(srow + ((c8 ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(3, kNumEpiThreads);
                 if (et == 0) {
-                    tma_store_2d(&tm_out, s.out_stage[buf], n0 + ch * 64, m0);
-                    bulk_commit_group();
+                    if (EPI != EPI_QUANT || p.out != nullptr) {
+                        tma_store_2d(&tm_out, s.out_stage[buf], n0 + ch * 64, m0);
+                        bulk_commit_group();
+                    }
+                    if constexpr (EPI == EPI_QUANT) {
+                        if (p.R_down > 0) {
+                            // next layer's low-rank down projection on the GELU output (no shift), lora.cuh:243-353:
+                            // D2[128 x Rdp] += G[128 x 64] * Ld_next[Rdp x 64]^T, staged tile doubles as the A operand
+                            tc_fence_after_sync();
+                            const uint32_t a_addr = smem_u32(s.out_stage[buf]);
+                            const uint32_t b_addr = smem_u32(s.ld_b + ch * kMaxRdp * 128);
+                            const uint32_t idesc_ld = make_idesc_f16(Tr::kIsBf16, BM, p.Rdp);
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                tc_mma_f16(tmem_base + C::kTmemLd, make_sw128_kmajor_desc(a_addr + j * 32),
+                                           make_sw128_kmajor_desc(b_addr + j * 32), idesc_ld, (ch | j) != 0);
+                            tc_commit(&s.stage_mma_done[buf]);
+                        }
+                    }
+                }
+                if constexpr (EPI == EPI_QUANT) {
+                    smd_phase[buf] ^= 1;
+                    // ---- next-layer quantisation of (gelu + shift) / smooth  (gemm_w4a4.cuh:930-1043) ---------
+                    const int m = m0 + row;
+                    uint8_t *qrow = p.qout + static_cast<size_t>(m) * (p.N >> 1) + ((n0 + ch * 64) >> 1);
+                    const float *smo = s.aux + ch * 64;
+                    if constexpr (!FP4) {
+                        typename Tr::T2 sh2;
+                        sh2.x = Tr::from_float(0.171875f);
+                        sh2.y = sh2.x;
+                        float amax = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const typename Tr::T2 gsh = __hadd2(*reinterpret_cast<typename Tr::T2 *>(&gw[i]), sh2);
+                            const float2 f = Tr::to_float2(gsh);
+                            const typename Tr::T2 d = Tr::from_float2(
+                                make_float2(__fdividef(f.x, smo[2 * i]), __fdividef(f.y, smo[2 * i + 1])));
+                            gw[i] = *reinterpret_cast<const uint32_t *>(&d);
+                            const float2 df = Tr::to_float2(d);
+                            amax = fmaxf(amax, fmaxf(fabsf(df.x), fabsf(df.y)));
+                        }
+                        const float s32 = amax * (1.0f / 15.0f);
+                        const float rs = rcp_approx_ftz(s32);
+                        reinterpret_cast<hT *>(p.oscales_out)[static_cast<size_t>((n0 >> 6) + ch) * p.Mp + m] = Tr::from_float(s32);
+                        uint32_t words[8];
+#pragma unroll
+                        for (int w8 = 0; w8 < 8; w8++) {
+                            int qv[8];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const float2 df = Tr::to_float2(*reinterpret_cast<typename Tr::T2 *>(&gw[w8 * 4 + i]));
+                                qv[2 * i] = cvt_rni(df.x * rs);
+                                qv[2 * i + 1] = cvt_rni(df.y * rs);
+                            }
+                            words[w8] = pack8_int4_b200<true>(qv);
+                        }
+                        *reinterpret_cast<uint4 *>(qrow) = make_uint4(words[0], words[1], words[2], words[3]);
+                        *reinterpret_cast<uint4 *>(qrow + 16) = make_uint4(words[4], words[5], words[6], words[7]);
+                    } else {
+                        uint32_t words[8];
+                        uint32_t sfw = 0;
+#pragma unroll
+                        for (int g16 = 0; g16 < 4; g16++) {
+                            float amax = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const int wi = g16 * 8 + i;
+                                const float2 f = Tr::to_float2(*reinterpret_cast<typename Tr::T2 *>(&gw[wi]));  // shift is 0 for FP4
+                                const typename Tr::T2 d = Tr::from_float2(
+                                    make_float2(__fdividef(f.x, smo[2 * wi]), __fdividef(f.y, smo[2 * wi + 1])));
+                                gw[wi] = *reinterpret_cast<const uint32_t *>(&d);
+                                const float2 df = Tr::to_float2(d);
+                                amax = fmaxf(amax, fmaxf(fabsf(df.x), fabsf(df.y)));
+                            }
+                            const float sc = fminf(amax * (1.0f / 6.0f), 448.0f);
+                            const float rs = rcp_approx_ftz(sc);
+                            sfw |= (cvt_e4m3x2(0.f, sc) & 0xFFu) << (8 * g16);
+#pragma unroll
+                            for (int w2 = 0; w2 < 2; w2++) {
+                                uint32_t wv = 0;
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    const float2 df = Tr::to_float2(*reinterpret_cast<typename Tr::T2 *>(&gw[g16 * 8 + w2 * 4 + i]));
+                                    wv |= cvt_e2m1x2(df.y * rs, df.x * rs) << (8 * i);
+                                }
+                                words[g16 * 2 + w2] = wv;
+                            }
+                        }
+                        *reinterpret_cast<uint4 *>(qrow) = make_uint4(words[0], words[1], words[2], words[3]);
+                        *reinterpret_cast<uint4 *>(qrow + 16) = make_uint4(words[4], words[5], words[6], words[7]);
+                        uint8_t *sf = reinterpret_cast<uint8_t *>(p.oscales_out) +
+                                      (static_cast<size_t>(m >> 7) * (p.N >> 6) + (n0 >> 6) + ch) * 512 + (m & 31) * 16 +
+                                      ((m & 127) >> 5) * 4;
+                        *reinterpret_cast<uint32_t *>(sf) = sfw;
+                    }
                 }
                 store_count++;
+            }
+            if constexpr (EPI == EPI_QUANT) {
+                if (p.R_down > 0) {
+                    if (et == 0) {
+                        tc_commit(&s.d2_full);
+                        tc_commit(&s.ld_b_empty);
+                    }
+                    mbar_wait(&s.d2_full, d2_phase);
+                    d2_phase ^= 1;
+                    tc_fence_after_sync();
+                    float *dst = p.lora_act_out + static_cast<size_t>(m0 + row) * p.R_down;
+                    for (int c16 = 0; c16 * 16 < p.Rdp; c16++) {
+                        uint32_t d2[16];
+                        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kTmemLd + c16 * 16, d2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            if (c16 * 16 + i < p.R_down) atomicAdd(dst + c16 * 16 + i, __uint_as_float(d2[i]));
+                    }
+                    tc_fence_before_sync();
+                }
             }
         }
         if (et == 0) bulk_wait_group<0>();
@@ -490,11 +715,11 @@ int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint
     return NB200_OK;
 }
 
-template <bool FP4, typename hT, int BN>
+template <bool FP4, typename hT, int BN, int EPI>
 int launch(const nb200_gemm_args &a, cudaStream_t stream) {
-    using C = Cfg<FP4, BN>;
-    using S = Smem<FP4, BN>;
-    CUtensorMap tm_act, tm_wgt, tm_out;
+    using C = Cfg<FP4, BN, EPI>;
+    using S = Smem<FP4, BN, EPI>;
+    CUtensorMap tm_act, tm_wgt, tm_out, tm_ld;
     const CUtensorMapSwizzle in_swz = FP4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
     const uint32_t in_box = FP4 ? 128 : 32;
     int rc = make_map_2d(&tm_act, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.act, a.K / 2, a.Mp, a.K / 2, in_box, BM, in_swz);
@@ -503,9 +728,22 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     if (rc) return rc;
     const CUtensorMapDataType odt =
         HalfTraits<hT>::kIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    rc = make_map_2d(&tm_out, odt, a.out, a.N_out, a.M_out, static_cast<uint64_t>(a.N_out) * 2, 64, BM,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+    if (a.out != nullptr) {
+        rc = make_map_2d(&tm_out, odt, a.out, a.N_out, a.M_out, static_cast<uint64_t>(a.N_out) * 2, 64, BM,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    } else {
+        tm_out = tm_act;  // never dereferenced
+    }
+    const int rdp = a.R_down;
+    if (EPI == EPI_QUANT && a.R_down > 0) {
+        rc = make_map_2d(&tm_ld, odt, a.lora_down_next, a.N, rdp, static_cast<uint64_t>(a.N) * 2, 64, rdp,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        NB200_CUDA_CHECK(cudaMemsetAsync(a.lora_act_out, 0, static_cast<size_t>(a.Mp) * a.R_down * sizeof(float), stream));
+    } else {
+        tm_ld = tm_act;
+    }
 
     GemmParams p;
     p.sfa = static_cast<const uint8_t *>(a.ascales);
@@ -527,6 +765,16 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.num_tiles = (a.Mp / BM) * p.num_n_blocks;
     p.mid_act = a.mid_act;
     p.act_unsigned = a.act_unsigned;
+    p.out = a.out;
+    p.qout = static_cast<uint8_t *>(a.qout);
+    p.oscales_out = a.oscales;
+    p.smooth_next = a.smooth_next;
+    p.lora_act_out = a.lora_act_out;
+    p.R_down = a.R_down;
+    p.Rdp = rdp;
+    p.norm_q = a.norm_q;
+    p.norm_k = a.norm_k;
+    p.rotary = a.rotary_emb;
     for (int i = 0; i < NB200_MAX_LORA_SCALES; i++) p.lora_scales[i] = a.lora_scales[i];
 
     static int num_sms_cached = 0;
@@ -538,13 +786,13 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     const int num_sms = a.num_sms > 0 ? a.num_sms : num_sms_cached;
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     const size_t smem_bytes = sizeof(S) + 1024;
-    auto kern = gemm_w4a4_kernel<FP4, hT, BN>;
+    auto kern = gemm_w4a4_kernel<FP4, hT, BN, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         NB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
         attr_set = true;
     }
-    kern<<<grid, C::kThreads, smem_bytes, stream>>>(tm_act, tm_wgt, tm_out, p);
+    kern<<<grid, C::kThreads, smem_bytes, stream>>>(tm_act, tm_wgt, tm_out, tm_ld, p);
     count_launch();
     NB200_CUDA_CHECK(cudaGetLastError());
     return NB200_OK;
@@ -552,10 +800,12 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
 
 template <bool FP4, typename hT>
 int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
+    if (a.qout != nullptr) return launch<FP4, hT, 128, EPI_QUANT>(a, stream);
+    if (a.rotary_emb != nullptr) return launch<FP4, hT, 128, EPI_ROPE>(a, stream);
     int bn = a.block_n;
     if (bn == 0) bn = (a.N % 256 == 0 && (a.Mp / BM) * (a.N / 256) >= 96) ? 256 : 128;
-    if (bn == 256 && a.N % 256 == 0) return launch<FP4, hT, 256>(a, stream);
-    if (bn == 128) return launch<FP4, hT, 128>(a, stream);
+    if (bn == 256 && a.N % 256 == 0) return launch<FP4, hT, 256, EPI_DEFAULT>(a, stream);
+    if (bn == 128) return launch<FP4, hT, 128, EPI_DEFAULT>(a, stream);
     return fail(NB200_ERR_INVALID_ARGUMENT, "block_n must be 0, 128 or 256 and divide N");
 }
 
@@ -574,15 +824,29 @@ extern "C" __attribute__((visibility("default"))) int nb200_gemm_w4a4(const nb20
     NB200_REQUIRE(a->R_up >= 0 && a->R_up % 16 == 0, "R_up must be a multiple of 16");
     NB200_REQUIRE((a->R_up == 0) || (a->lora_act_in && a->lora_up), "lora_act_in and lora_up go together");
     NB200_REQUIRE(a->R_up <= 16 * NB200_MAX_LORA_SCALES, "rank exceeds MAX_RANK (1024)");
-    if (a->qout != nullptr || a->rotary_emb != nullptr || a->lora_down_next != nullptr)
-        return fail(NB200_ERR_UNSUPPORTED, "fused next-layer quantize / RMSNorm+RoPE epilogues are not built yet");
-    NB200_REQUIRE(a->out != nullptr, "out must be non-NULL");
-    NB200_REQUIRE(a->M_out > 0 && a->M_out <= a->Mp && a->Mp - a->M_out < 256, "M_out must be in (Mp-256, Mp]");
-    NB200_REQUIRE(a->N_out > 0 && a->N_out <= a->N && a->N - a->N_out < 128, "N_out must be in (N-128, N]");
-    NB200_REQUIRE(a->N_out % 8 == 0, "out row pitch must be a multiple of 16 bytes (TMA store)");
-    NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->act) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->wgt) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
-                  "act/wgt/out must be 16-byte aligned");
+    NB200_REQUIRE(a->out != nullptr || a->qout != nullptr, "out or qout must be non-NULL");
+    if (a->qout != nullptr) {
+        // fc1 -> GELU -> (lora_down of fc2) -> quantise for fc2   (launch_impl:282-310)
+        NB200_REQUIRE(a->oscales && a->smooth_next, "qout needs oscales and smooth_next");
+        NB200_REQUIRE(a->rotary_emb == nullptr, "qout and rotary_emb are exclusive");
+        NB200_REQUIRE(a->R_down >= 0 && a->R_down % 16 == 0, "R_down must be a multiple of 16");
+        if (a->R_down > kMaxRdp)
+            return fail(NB200_ERR_UNSUPPORTED, "fused next-layer low-rank down projection supports rank <= 128");
+        NB200_REQUIRE(a->R_down == 0 || (a->lora_down_next && a->lora_act_out), "lora_down_next and lora_act_out go together");
+        NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->qout) & 15) == 0, "qout must be 16-byte aligned");
+    }
+    if (a->rotary_emb != nullptr) {
+        NB200_REQUIRE(a->norm_q && a->norm_k && a->out, "rotary_emb needs norm_q, norm_k and out");
+        NB200_REQUIRE(a->N % 384 == 0, "RMSNorm+RoPE epilogue: N must be 3 * heads * 128");
+    }
+    if (a->out != nullptr) {
+        NB200_REQUIRE(a->M_out > 0 && a->M_out <= a->Mp && a->Mp - a->M_out < 256, "M_out must be in (Mp-256, Mp]");
+        NB200_REQUIRE(a->N_out > 0 && a->N_out <= a->N && a->N - a->N_out < 128, "N_out must be in (N-128, N]");
+        NB200_REQUIRE(a->N_out % 8 == 0, "out row pitch must be a multiple of 16 bytes (TMA store)");
+        NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "out must be 16-byte aligned");
+    }
+    NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->act) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->wgt) & 15) == 0,
+                  "act/wgt must be 16-byte aligned");
     NB200_REQUIRE(a->fp4 || !a->cscale, "INT4 path has no per-channel scale (alpha == 1, launch_impl:107)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (a->fp4) {

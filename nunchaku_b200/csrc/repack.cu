@@ -150,6 +150,19 @@ __global__ void repack_lora_down_kernel(const hT *__restrict__ src, hT *__restri
     }
 }
 
+// dst = logical Ld[r][k] row-major [R][K]: the TMA source of the fused next-layer down projection
+template <typename hT>
+__global__ void repack_lora_down_rowmajor_kernel(const hT *__restrict__ src, hT *__restrict__ dst, int K, int R) {
+    const size_t total = static_cast<size_t>(K) * R;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / K), k = static_cast<int>(i % K);
+        const int u = r >> 4, h = (r >> 3) & 1, g = r & 7;
+        const int ii = k >> 4, c = (k >> 3) & 1, tt = (k >> 1) & 3, e = k & 1;
+        dst[i] = src[ref_lowrank_index(ii, u, g, tt, h, c, e, R)];
+    }
+}
+
 inline int grid_for(size_t total) {
     size_t b = (total + kThreads - 1) / kThreads;
     return static_cast<int>(b > 148 * 16 ? 148 * 16 : (b == 0 ? 1 : b));
@@ -245,6 +258,23 @@ extern "C" __attribute__((visibility("default"))) int nb200_repack_lora_down(con
     else
         repack_lora_down_kernel<__half><<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __half *>(src), static_cast<__half *>(dst), K, R, Rp);
+    count_launch();
+    NB200_CUDA_CHECK(cudaGetLastError());
+    return NB200_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int nb200_repack_lora_down_next(const void *src, void *dst, int K, int R, int dtype, void *stream) {
+    reset_launch_count();
+    NB200_REQUIRE(src && dst, "NULL tensor");
+    NB200_REQUIRE(K % 16 == 0 && R % 16 == 0 && R > 0, "K % 16 == 0, R % 16 == 0, R > 0 required");
+    NB200_REQUIRE(dtype == NB200_FP16 || dtype == NB200_BF16, "dtype must be fp16 or bf16");
+    const size_t total = static_cast<size_t>(K) * R;
+    if (dtype == NB200_BF16)
+        repack_lora_down_rowmajor_kernel<__nv_bfloat16><<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16 *>(src), static_cast<__nv_bfloat16 *>(dst), K, R);
+    else
+        repack_lora_down_rowmajor_kernel<__half><<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __half *>(src), static_cast<__half *>(dst), K, R);
     count_launch();
     NB200_CUDA_CHECK(cudaGetLastError());
     return NB200_OK;

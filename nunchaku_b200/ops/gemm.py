@@ -62,10 +62,19 @@ def svdq_gemm_w4a4_cuda(
         raise NotImplementedError("SANA LiteLA epilogue (out_vk/out_linearattn) is not built yet")
     if out_q is not None or out_k is not None or out_v is not None:
         raise NotImplementedError("PackQKV epilogue (out_q/out_k/out_v) is not built yet")
-    if qout is not None or oscales is not None or rotary_emb is not None or lora_down is not None:
-        raise NotImplementedError("fused next-layer quantize / RMSNorm+RoPE epilogues are not built yet")
-    if out is None:
-        raise ValueError("out is required")
+    fused_quant = qout is not None and oscales is not None          # launch_impl:282
+    if (qout is None) != (oscales is None):
+        raise ValueError("qout and oscales go together")
+    if out is None and not fused_quant:
+        raise ValueError("out is required unless qout/oscales are given")
+    if fused_quant and smooth_factor is None:
+        raise ValueError("qout needs smooth_factor (the next layer's smoothing vector)")
+    if (lora_down is None) != (lora_act_out is None):
+        raise ValueError("lora_down and lora_act_out go together (launch_impl:199)")
+    if lora_down is not None and not fused_quant:
+        raise NotImplementedError("lora_down/lora_act_out are only wired for the fused quantize epilogue (as in the reference's callers)")
+    if rotary_emb is not None and (norm_q is None or norm_k is None):
+        raise ValueError("rotary_emb needs norm_q and norm_k (launch_impl:348-349)")
     if alpha is None:
         alpha = 1.0
     if not fp4 and float(alpha) != 1.0:
@@ -76,8 +85,8 @@ def svdq_gemm_w4a4_cuda(
     N = wgt.shape[0]
     if wgt.shape[1] * 2 != K:
         raise ValueError("act and wgt disagree on K")
-    out2d = out.view(-1, out.shape[-1])
-    dtype = out.dtype
+    out2d = None if out is None else out.view(-1, out.shape[-1])
+    dtype = out.dtype if out is not None else (bias.dtype if bias is not None else lora_up.dtype)
 
     args = GemmArgs()
     args.act = act.data_ptr()
@@ -105,10 +114,27 @@ def svdq_gemm_w4a4_cuda(
         lora_scales = [1.0] * math.ceil(rank / 16)
     for i in range(NB200_MAX_LORA_SCALES):  # absent groups get 0 (launch_impl:220-225)
         args.lora_scales[i] = float(lora_scales[i]) if i < len(lora_scales) else 0.0
-    args.out = out2d.data_ptr()
     args.Mp, args.N, args.K = Mp, N, K
-    args.M_out, args.N_out = out2d.shape[0], out2d.shape[1]
+    if out2d is not None:
+        args.out = out2d.data_ptr()
+        args.M_out, args.N_out = out2d.shape[0], out2d.shape[1]
     args.R_up, args.R_down = rank, 0
+    if fused_quant:
+        assert qout.shape[-1] * 2 == N and qout.numel() // qout.shape[-1] == Mp and qout.is_contiguous()
+        args.qout = qout.data_ptr()
+        args.oscales = oscales.data_ptr()
+        args.smooth_next = repack.channel_vector(smooth_factor, out_f32=False).data_ptr()
+        if lora_down is not None and lora_down.shape[1] > 0:
+            assert lora_act_out.dtype == torch.float32 and lora_act_out.shape == (Mp, lora_down.shape[1])
+            args.lora_down_next = repack.lora_down_next(lora_down).data_ptr()
+            args.lora_act_out = lora_act_out.data_ptr()
+            args.R_down = lora_down.shape[1]
+    if rotary_emb is not None:
+        assert rotary_emb.dtype == torch.float32 and rotary_emb.numel() == Mp * 128, "rotary_emb: packed fp32 [Mp, 128]"
+        assert norm_q.numel() == 128 and norm_k.numel() == 128
+        args.rotary_emb = rotary_emb.data_ptr()
+        args.norm_q = norm_q.contiguous().data_ptr()
+        args.norm_k = norm_k.contiguous().data_ptr()
     args.dtype = torch_dtype_code(dtype)
     args.fp4 = int(fp4)
     args.act_unsigned = int(act_unsigned)

@@ -137,3 +137,17 @@ def lora_down(ld: torch.Tensor) -> torch.Tensor:
     check(lib.nb200_repack_lora_down(ld.data_ptr(), out.data_ptr(), K, R, torch_dtype_code(ld.dtype), _stream()),
           "repack_lora_down")
     return _store("lora_down", ld, sig, out)
+
+
+def lora_down_next(ld: torch.Tensor) -> torch.Tensor:
+    """reference [K, R] -> logical [R, K] row-major: TMA source of the fused fc1->fc2 down projection."""
+    _require_cuda(ld, "lora_down")
+    sig = _sig(ld)
+    hit = _lookup("lora_down_next", ld, sig)
+    if hit is not None:
+        return hit
+    K, R = ld.shape
+    out = torch.empty(R, K, dtype=ld.dtype, device=ld.device)
+    check(lib.nb200_repack_lora_down_next(ld.data_ptr(), out.data_ptr(), K, R, torch_dtype_code(ld.dtype), _stream()),
+          "repack_lora_down_next")
+    return _store("lora_down_next", ld, sig, out)

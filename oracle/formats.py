@@ -35,6 +35,7 @@ __all__ = [
     "lowrank_flat_index",
     "pack_lowrank",
     "unpack_lowrank",
+    "pack_rotemb",
 ]
 
 
@@ -214,3 +215,25 @@ def unpack_lowrank(stored: torch.Tensor, down: bool) -> torch.Tensor:
     C, R = stored.shape
     idx = lowrank_flat_index(C, R, down, stored.device)
     return stored.reshape(-1)[idx.reshape(-1)].view(idx.shape)
+
+
+# --------------------------------------------------------------------------------------
+# A.4  packed rotary table; nunchaku/models/embeddings.py (pack_rotemb) and
+#   nunchaku/models/transformers/transformer_flux.py:60-92; consumed by EpilogueRMSNormRope::load_rotemb
+#   (epilogues.cuh:283-300): fp32 accumulator-fragment order, one float4 = {sin,cos of row g, sin,cos of row g+8}
+# --------------------------------------------------------------------------------------
+def pack_rotemb(sin: torch.Tensor, cos: torch.Tensor) -> torch.Tensor:
+    """sin, cos: logical [M, 64] fp32 (pair i rotates head columns 2i, 2i+1) -> packed [M, 128] fp32.
+
+    float index of (m, pair p, s) with s = 0 (sin) / 1 (cos):
+        (((((m/16)*16 + p/4)*8 + m%8)*4 + p%4)*2 + (m%16)/8)*2 + s
+    """
+    M, P = sin.shape
+    assert P == 64 and M % 16 == 0
+    m = torch.arange(M, device=sin.device).view(M, 1, 1)
+    p = torch.arange(64, device=sin.device).view(1, 64, 1)
+    s = torch.arange(2, device=sin.device).view(1, 1, 2)
+    idx = (((((m // 16) * 16 + p // 4) * 8 + m % 8) * 4 + p % 4) * 2 + (m % 16) // 8) * 2 + s
+    out = torch.empty(M * 128, dtype=torch.float32, device=sin.device)
+    out[idx.reshape(-1)] = torch.stack([sin, cos], dim=-1).to(torch.float32).reshape(-1)
+    return out.view(M, 128)

@@ -88,6 +88,20 @@ def main():
     # reference unpack must invert its own pack (sanity of the fixture itself)
     assert torch.equal(packer.unpack_lowrank_weight(pd, down=True), down)
 
+    # ---- packed rotary table: pack_rotemb (nunchaku/models/embeddings.py) ----
+    # the module imports diffusers at top level (absent here), so only the function's own source
+    # is executed, straight from the reference file (nothing is copied into this repo)
+    import ast
+
+    src_path = os.path.join(REF, "nunchaku/models/embeddings.py")
+    tree = ast.parse(open(src_path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "pack_rotemb")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), src_path, "exec"), ns)
+    rot = torch.randn((1, 32, 64, 1, 2), generator=g, dtype=torch.float32)   # (B, M, D/2, 1, 2) = (sin, cos)
+    out["rotemb_m32"] = rot.numpy()
+    out["rotemb_m32_packed"] = ns["pack_rotemb"](rot.clone()).numpy()
+
     path = os.path.join(HERE, "packer_formats.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: v.shape for k, v in out.items()}, os.path.getsize(path), "bytes")

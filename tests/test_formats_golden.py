@@ -65,3 +65,10 @@ def test_roundtrips_random_shapes():
         assert torch.equal(F.unpack_group_scales(F.pack_group_scales(s)), s)
         m = torch.randint(0, 127, (N, K // 16), generator=g, dtype=torch.uint8)
         assert torch.equal(F.unpack_micro_scales(F.pack_micro_scales(m)), m)
+
+
+def test_pack_rotemb_matches_reference():
+    rot = torch.from_numpy(GOLD["rotemb_m32"])            # (1, M, 64, 1, 2) = (sin, cos)
+    ref = torch.from_numpy(GOLD["rotemb_m32_packed"])     # (1, M, 128)
+    sin, cos = rot[0, :, :, 0, 0], rot[0, :, :, 0, 1]
+    assert torch.equal(F.pack_rotemb(sin, cos), ref[0])

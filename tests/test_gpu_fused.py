@@ -1,0 +1,181 @@
+"""GPU parity of the fused GEMM epilogues (through the C ABI) against the CPU oracle:
+  * fc1 -> GELU -> [next layer's lora_down] -> 4-bit quantise for fc2   (launch_impl:282-310)
+  * QKV projection -> per-head RMSNorm(Q, K) -> RoPE                      (launch_impl:347-406)
+
+Tolerances:
+  * `out` (the hT GELU / RoPE tile): same gates as test_gpu_gemm (1e-2 vs the reference-emulating
+    oracle, 4e-3 / 1.5e-3 vs fp64 for bf16 / fp16; tanh.approx / rsqrt.approx add < 1e-3);
+  * next-layer codes: re-derived by the ORACLE's quantiser from the kernel's own stored hT tile, so
+    only tie flips of the approximate reciprocal remain: scales bit-exact, code mismatch fraction
+    <= 2e-3, |step| <= 1;
+  * lora_act_out vs fp64 matmul of the stored tile: rel-Frobenius <= 1e-4 (fp32 atomics order).
+"""
+import pytest
+import torch
+
+import b200_layouts as L
+from gpu_util import diag, ref_layout_params
+from oracle import formats as F
+from oracle import svdq as O
+from test_gpu_gemm import _assert_parity, _record
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack_act(qa, fp4, hT):
+    Mp, K = qa.q.shape
+    if fp4:
+        return (L.pack_fp4(qa.q).cuda(),
+                L.pack_sf_tiles(qa.scales.t().contiguous()).view(torch.float8_e4m3fn).view(K // 16, Mp).cuda())
+    return L.pack_int4(qa.q, signed=True).cuda(), qa.scales.cuda()
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("with_out,R2", [(True, 32), (False, 16), (True, 0)])
+def test_fused_gelu_quantize_next(fp4, hT, with_out, R2):
+    from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
+
+    N, K, R, M = 384, 256, 32, 300
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=51)
+    g = torch.Generator().manual_seed(52)
+    nxt_smooth = (torch.rand(N, generator=g) + 0.5).to(hT)
+    nxt_ld = (torch.randn(max(R2, 16), N, generator=g) * 0.05).to(hT)[:R2] if R2 else None
+    x = O.make_activations(M, K, hT, seed=53, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=fp4)
+    Mp = qa.q.shape[0]
+    params = ref_layout_params(layer)
+    act, asc = _pack_act(qa, fp4, hT)
+    out = torch.full((M, N), float("nan"), dtype=hT, device="cuda") if with_out else None
+    qout = torch.zeros(Mp, N // 2, dtype=torch.uint8, device="cuda")
+    osc = (torch.zeros(N // 16, Mp, dtype=torch.float8_e4m3fn, device="cuda") if fp4
+           else torch.zeros(N // 64, Mp, dtype=hT, device="cuda"))
+    la_out = torch.full((Mp, R2), float("nan"), dtype=torch.float32, device="cuda") if R2 else None
+    svdq_gemm_w4a4_cuda(
+        act=act, wgt=params["qweight"], out=out, qout=qout, ascales=asc, wscales=params["wscales"], oscales=osc,
+        lora_act_in=qa.lora_act.cuda(), lora_up=params["proj_up"],
+        lora_down=F.pack_lowrank(nxt_ld, down=True).cuda() if R2 else None, lora_act_out=la_out,
+        bias=params["bias"], smooth_factor=F.pack_channel_vector(nxt_smooth).cuda(), fp4=fp4, alpha=layer.alpha,
+        wcscales=params["wcscales"])
+    torch.cuda.synchronize()
+
+    kw = dict(qa=qa.q, ascales=qa.scales, qw=layer.qw, wscales=layer.wscales, hT=hT, M=M, bias=layer.bias,
+              lora_act=qa.lora_act, lora_up=layer.lora_up, fp4=fp4, alpha=layer.alpha, wcscales=layer.wcscales,
+              act="gelu", next_smooth=nxt_smooth, next_lora_down=nxt_ld)
+    r_ref, r_ex = O.gemm_w4a4(mode="ref", **kw), O.gemm_w4a4(mode="exact", **kw)
+    name = f"fused gelu+quant fp4={fp4} {hT} out={with_out} R2={R2}"
+    if with_out:
+        _assert_parity(out, r_ex.out, r_ref.out, hT, name)
+        # re-derive the next layer's operands from the tile the kernel itself stored
+        g_h = torch.zeros(Mp, N, dtype=hT)
+        g_h[:M] = out.cpu()
+        shift = 0.0 if fp4 else O.SHIFT_GELU
+        ys = O.h_div(O.rn(g_h.double() + shift, hT), nxt_smooth.view(1, N))
+        q_exp, s_exp = (O._quantize_rows_fp4(ys) if fp4 else O._quantize_rows_int4(ys, unsigned=True))
+        if fp4:
+            codes = L.unpack_fp4(qout.cpu())[:M]
+            scales = L.unpack_sf_tiles(osc.cpu().view(torch.uint8).reshape(-1), Mp, N // 16).t().contiguous()[:, :M]
+            assert torch.equal(scales, s_exp[:, :M]), diag("next scales", scales.float(), s_exp[:, :M].float())
+            nz = (O.e4m3_decode(s_exp[:, :M]).t() != 0).repeat_interleave(16, dim=1)
+            cmp = O.compare_codes(codes[nz], q_exp[:M][nz], fp4=True)
+        else:
+            codes = L.unpack_int4(qout.cpu(), signed=False)[:M]
+            assert torch.equal(osc.cpu()[:, :M].view(torch.int16), s_exp[:, :M].view(torch.int16)), \
+                diag("next scales", osc.float()[:, :M], s_exp[:, :M].float())
+            cmp = O.compare_codes(codes, q_exp[:M], fp4=False)
+        assert cmp["frac"] <= 2e-3 and cmp["max_step"] <= 1, (name, cmp)
+        if R2:
+            exp_la = g_h[:M].double() @ nxt_ld.double().t()
+            e = O.rel_fro(la_out.cpu()[:M], exp_la)
+            assert e <= 1e-4, diag("lora_act_out", la_out[:M], exp_la)
+    else:
+        # no stored tile: compare dequantised next-layer input and low-rank state with the oracle
+        if fp4:
+            deq = O.dequant(L.unpack_fp4(qout.cpu()), L.unpack_sf_tiles(osc.cpu().view(torch.uint8).reshape(-1), Mp, N // 16), True)[:M]
+        else:
+            deq = O.dequant(L.unpack_int4(qout.cpu(), signed=False), osc.cpu().t().contiguous(), False)[:M]
+        deq_ref = O.dequant(r_ex.qout, r_ex.oscales.t().contiguous(), fp4)[:M]
+        e = O.rel_fro(deq, deq_ref)
+        _record(name + " deq", dtype=str(hT), ours_vs_exact=e)
+        assert e <= 3e-2, diag("next act (dequantised)", deq, deq_ref)
+        if R2:
+            e2 = O.rel_fro(la_out.cpu()[:M], r_ex.lora_act_out[:M])
+            assert e2 <= 1e-2, diag("lora_act_out", la_out[:M], r_ex.lora_act_out[:M])
+
+
+@pytest.mark.parametrize("precision", ["int4", "nvfp4"])
+def test_fused_gelu_mlp_module_chain(precision):
+    """fused_gelu_mlp(x, fc1, fc2) (ops/fused.py:14-79) end to end vs the oracle chain."""
+    from nunchaku_b200.models.linear import SVDQW4A4Linear
+    from nunchaku_b200.ops.fused import fused_gelu_mlp
+
+    fp4 = precision == "nvfp4"
+    hT = torch.bfloat16
+    D, H, R, M = 256, 512, 32, 200
+    l1 = O.make_synthetic_layer(H, D, R, fp4=fp4, hT=hT, seed=61)
+    l2 = O.make_synthetic_layer(D, H, R, fp4=fp4, hT=hT, seed=62)
+    x = O.make_activations(M, D, hT, seed=63, smooth=l1.smooth)
+
+    def mk(layer, K, N, unsigned):
+        p = ref_layout_params(layer)
+        m = SVDQW4A4Linear(K, N, rank=R, bias=True, precision=precision, act_unsigned=unsigned, torch_dtype=hT, device="cuda")
+        sd = {"qweight": p["qweight"], "wscales": p["wscales"], "bias": p["bias"], "smooth_factor": p["smooth"],
+              "smooth_factor_orig": p["smooth"], "proj_down": p["proj_down"], "proj_up": p["proj_up"]}
+        if fp4:
+            sd["wcscales"] = p["wcscales"]
+            m.wtscale = layer.alpha
+        m.load_state_dict(sd)
+        return m
+
+    fc1, fc2 = mk(l1, D, H, False), mk(l2, H, D, not fp4)
+    y = fused_gelu_mlp(x.cuda().view(1, M, D), fc1, fc2).view(M, D)
+    torch.cuda.synchronize()
+    qa = O.quantize_w4a4_act_fuse_lora(x, l1.smooth, l1.lora_down, fp4=fp4)
+    outs = {}
+    for mode in ("ref", "exact"):
+        r1 = O.gemm_w4a4(qa=qa.q, ascales=qa.scales, qw=l1.qw, wscales=l1.wscales, hT=hT, M=M, bias=l1.bias,
+                         lora_act=qa.lora_act, lora_up=l1.lora_up, fp4=fp4, alpha=l1.alpha, wcscales=l1.wcscales,
+                         act="gelu", next_smooth=l2.smooth, next_lora_down=l2.lora_down, want_out=False, mode=mode)
+        outs[mode] = O.gemm_w4a4(qa=r1.qout, ascales=r1.oscales, qw=l2.qw, wscales=l2.wscales, hT=hT, M=M, bias=l2.bias,
+                                 lora_act=r1.lora_act_out, lora_up=l2.lora_up, fp4=fp4, alpha=l2.alpha,
+                                 wcscales=l2.wcscales, mode=mode).out
+    e_ref, e_ex = O.rel_fro(y.cpu(), outs["ref"]), O.rel_fro(y.cpu(), outs["exact"])
+    _record(f"fused_gelu_mlp {precision}", dtype=str(hT), ours_vs_exact=e_ex, ours_vs_ref=e_ref,
+            ref_vs_exact=O.rel_fro(outs["ref"], outs["exact"]))
+    # two quantisers in the chain: tie flips of the intermediate 4-bit codes dominate (see test_gpu_gemm)
+    assert e_ref <= 3e-2 and e_ex <= 3e-2, f"{precision}: vs ref {e_ref:.3e} vs exact {e_ex:.3e}\n" + diag("mlp", y, outs["exact"])
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+def test_qkv_rmsnorm_rope(fp4, hT):
+    from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
+
+    H, K, R, M = 2, 256, 32, 300
+    N = 3 * H * 128
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=71)
+    g = torch.Generator().manual_seed(72)
+    norm_q = (1.0 + 0.2 * torch.randn(128, generator=g)).to(hT)
+    norm_k = (1.0 + 0.2 * torch.randn(128, generator=g)).to(hT)
+    x = O.make_activations(M, K, hT, seed=73, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=fp4)
+    Mp = qa.q.shape[0]
+    ang = torch.rand(Mp, 64, generator=g) * 6.283
+    rsin, rcos = torch.sin(ang), torch.cos(ang)
+    params = ref_layout_params(layer)
+    act, asc = _pack_act(qa, fp4, hT)
+    out = torch.full((M, N), float("nan"), dtype=hT, device="cuda")
+    svdq_gemm_w4a4_cuda(act=act, wgt=params["qweight"], out=out, ascales=asc, wscales=params["wscales"],
+                        lora_act_in=qa.lora_act.cuda(), lora_up=params["proj_up"], bias=params["bias"], fp4=fp4,
+                        alpha=layer.alpha, wcscales=params["wcscales"], norm_q=norm_q.cuda(), norm_k=norm_k.cuda(),
+                        rotary_emb=F.pack_rotemb(rsin, rcos).cuda())
+    torch.cuda.synchronize()
+    kw = dict(qa=qa.q, ascales=qa.scales, qw=layer.qw, wscales=layer.wscales, hT=hT, M=M, bias=layer.bias,
+              lora_act=qa.lora_act, lora_up=layer.lora_up, fp4=fp4, alpha=layer.alpha, wcscales=layer.wcscales,
+              rope=(norm_q, norm_k, rsin, rcos))
+    y_ref, y_ex = O.gemm_w4a4(mode="ref", **kw).out, O.gemm_w4a4(mode="exact", **kw).out
+    _assert_parity(out, y_ex, y_ref, hT, f"qkv rmsnorm+rope fp4={fp4} {hT}")
+    # V third untouched by norm/rope: equals the plain epilogue
+    kw.pop("rope")
+    v_ex = O.gemm_w4a4(mode="exact", **kw).out[:, 2 * N // 3:]
+    assert O.rel_fro(out.cpu()[:, 2 * N // 3:], v_ex) <= (4e-3 if hT == torch.bfloat16 else 1.5e-3)
