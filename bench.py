@@ -4,7 +4,8 @@
 A "step" is one denoising step's worth of the hot path: every SVDQuant linear of the
 FLUX.1-schnell transformer (19 joint blocks x {qkv, out, fc1, fc2} for the 4096-token image
 stream and the 256-token text stream, 38 single blocks x {qkv, out, fc1, fc2} on 4352 tokens)
-= 304 fused W4A4 GEMM launches + their activation-quantize launches, at the model's exact shapes,
+= 304 fused W4A4 GEMM launches + 228 activation-quantize launches (fc2's input is quantised inside
+fc1's GEMM epilogue, as in the reference), at the model's exact shapes,
 rank 32, synthetic random-init 4-bit weights (no checkpoints offline) and synthetic activations.
 Attention / AdaLN / elementwise glue are outside the hot path and not run.
 An image is 4 steps.  value = images/s of this stack, whole job over all ranks.
@@ -117,7 +118,9 @@ def build_stack(torch, precision: str, dtype, device):
     g = torch.Generator(device=device).manual_seed(1234)
     mods = []
     for tag, M, K, N, act in layer_list():
-        m = SVDQW4A4Linear(K, N, rank=RANK, bias=True, precision=precision, torch_dtype=dtype, device=device)
+        # fc2 consumes the fused fc1 epilogue's UNSIGNED (shifted GELU) INT4 activations (attention.py:98-99)
+        m = SVDQW4A4Linear(K, N, rank=RANK, bias=True, precision=precision, torch_dtype=dtype, device=device,
+                           act_unsigned=(tag.endswith("fc2") and not fp4))
         with torch.no_grad():
             # the packed layouts are permutations: random bytes in the reference layout ARE random weights
             m.qweight.copy_(torch.randint(-128, 128, m.qweight.shape, generator=g, device=device, dtype=torch.int8))
@@ -165,6 +168,7 @@ class StackRunner:
             if (M, N) not in self.y:
                 self.y[(M, N)] = torch.empty(M, N, dtype=dtype, device=device)
         self.gemm_events = None
+        self.launches = 0
 
     def set_inputs(self, img, txt):
         """e2e: refresh the step's inputs (the image/text stream activations)."""
@@ -172,22 +176,51 @@ class StackRunner:
         self.x[(TXT_TOKENS, DIM)].copy_(txt, non_blocking=True)
 
     def step(self, record_gemm_events=False):
+        """qkv, out: quantize + GEMM.  fc1 -> fc2: quantize + fused GEMM (GELU, fc2's low-rank down
+        projection and fc2's 4-bit activations produced in fc1's epilogue; the [M, 12288] tensor never
+        reaches HBM) + GEMM -- the reference's launch structure (FluxModel.cpp:16-20): 304 GEMMs and 228
+        quantizes per step."""
         torch = self.torch
         ev = [] if record_gemm_events else None
-        for _, M, K, N, act, m in self.mods:
+
+        def timed(fn, flops):
+            if ev is None:
+                fn()
+                return
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            ev.append((e0, e1, flops))
+
+        mods = self.mods
+        i = 0
+        while i < len(mods):
+            tag, M, K, N, act, m = mods[i]
             q, s, la = self.q[(M, K)]
             fp4 = m.precision == "nvfp4"
             self.quant(self.x[(M, K)], output=q, oscales=s, lora_down=m.proj_down, lora_act_out=la,
                        smooth=m.smooth_factor, fp4=fp4)
-            if ev is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            self.gemm(act=q, wgt=m.qweight, out=self.y[(M, N)], ascales=s, wscales=m.wscales, lora_act_in=la,
-                      lora_up=m.proj_up, bias=m.bias, fp4=fp4, alpha=m.wtscale, wcscales=m.wcscales,
-                      fuse_silu=False)
-            if ev is not None:
-                e1.record()
-                ev.append((e0, e1, 2 * M * K * N + 2 * M * RANK * N))
+            self.launches += 1
+            if tag.endswith("fc1"):
+                _, _, K2, N2, _, m2 = mods[i + 1]
+                q2, s2, la2 = self.q[(M, K2)]
+                timed(lambda: self.gemm(act=q, wgt=m.qweight, qout=q2, ascales=s, wscales=m.wscales, oscales=s2,
+                                        lora_act_in=la, lora_up=m.proj_up, lora_down=m2.proj_down, lora_act_out=la2,
+                                        bias=m.bias, smooth_factor=m2.smooth_factor, fp4=fp4, alpha=m.wtscale,
+                                        wcscales=m.wcscales), 2 * M * K * N + 2 * M * RANK * N + 2 * M * RANK * N)
+                timed(lambda: self.gemm(act=q2, wgt=m2.qweight, out=self.y[(M, N2)], ascales=s2, wscales=m2.wscales,
+                                        lora_act_in=la2, lora_up=m2.proj_up, bias=m2.bias, fp4=fp4, alpha=m2.wtscale,
+                                        wcscales=m2.wcscales, act_unsigned=m2.act_unsigned),
+                      2 * M * K2 * N2 + 2 * M * RANK * N2)
+                self.launches += 2
+                i += 2
+            else:
+                timed(lambda: self.gemm(act=q, wgt=m.qweight, out=self.y[(M, N)], ascales=s, wscales=m.wscales,
+                                        lora_act_in=la, lora_up=m.proj_up, bias=m.bias, fp4=fp4, alpha=m.wtscale,
+                                        wcscales=m.wcscales), 2 * M * K * N + 2 * M * RANK * N)
+                self.launches += 1
+                i += 1
         self.gemm_events = ev
         return self.y[(IMG_TOKENS + TXT_TOKENS, DIM)]
 
@@ -293,7 +326,9 @@ def main() -> int:
 
     # ---- warm-up (also triggers the one-time repack) -----------------------------------------
     for _ in range(args.warmup):
+        runner.launches = 0
         runner.step()
+    launches_per_step = runner.launches   # our kernels only (quantize + gemm; the fused fc1 memset is a driver memset node)
     torch.cuda.synchronize()
 
     # ---- device-resident throughput: captured CUDA graph of one step ---------------------------
@@ -399,7 +434,7 @@ def main() -> int:
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_images, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": "SVDQW4A4 ops (quantize + gemm) launched from Python per layer, pinned host in/out"},
-            "gpu_launches": args.steps * 2 * n_layers,
+            "gpu_launches": args.steps * launches_per_step,
             "roofline": roofline,
             "cpu_baseline": cpu,
         }

@@ -89,7 +89,8 @@ int nb200_repack_channel_vector(const void *src, void *dst, int N, int dtype, in
  * (cscale may be NULL == 1).  dst holds N * Rp elements, Rp = ceil(R/32)*32. */
 int nb200_repack_lora_up(const void *src, void *dst, const float *cscale, int N, int R, int dtype, void *stream);
 /* lora_down: reference hT [K, R] -> B200 fragment order for the quantize kernel
- * (dst holds K * Rp elements, Rp = ceil(R/32)*32). */
+ * (dst holds 2 * K * Rp elements, Rp = ceil(R/32)*32: the TMA kernel's true-k-order fragments
+ * followed by the register-streaming (GLU) kernel's k-permuted fragments). */
 int nb200_repack_lora_down(const void *src, void *dst, int K, int R, int dtype, void *stream);
 /* lora_down of the NEXT layer for the fused fc1 epilogue: reference hT [K, R] -> logical [R, K]
  * row-major (TMA source; K here is the fc1 output width N). */
@@ -110,7 +111,14 @@ typedef struct nb200_quantize_args {
     int dtype;             /* nb200_dtype                                                  */
     int fuse_glu;
     int fp4;
+    /* optional scratch for the small-M split-K path (deterministic last-block reduction); NULL
+     * disables the split.  nb200_quantize_workspace_bytes() gives a sufficient size.  Must be
+     * zero-initialised once; the kernel leaves it clean. */
+    void *workspace;
+    long long workspace_bytes;
 } nb200_quantize_args;
+
+long long nb200_quantize_workspace_bytes(int Mp, int K);
 
 int nb200_quantize_w4a4_act_fuse_lora(const nb200_quantize_args *args, void *stream);
 

@@ -34,6 +34,8 @@ class QuantizeArgs(ctypes.Structure):
         ("dtype", c_int),
         ("fuse_glu", c_int),
         ("fp4", c_int),
+        ("workspace", c_void_p),
+        ("workspace_bytes", ctypes.c_longlong),
     ]
 
 
@@ -86,6 +88,7 @@ SYMBOLS = {
     "nb200_repack_lora_up": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "nb200_repack_lora_down": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "nb200_repack_lora_down_next": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "nb200_quantize_workspace_bytes": (ctypes.c_longlong, [c_int, c_int]),
     "nb200_quantize_w4a4_act_fuse_lora": (c_int, [ctypes.POINTER(QuantizeArgs), c_void_p]),
     "nb200_gemm_w4a4": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
 }

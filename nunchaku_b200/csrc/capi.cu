@@ -1,4 +1,8 @@
 // C-ABI glue shared by all translation units: error string, launch counter, device check.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
 
 namespace nb200 {
@@ -17,6 +21,39 @@ int fail(int code, const std::string &msg) {
 
 void count_launch(int n) { g_launches += n; }
 void reset_launch_count() { g_launches = 0; }
+
+// ---- TMA tensor maps (driver entry point resolved through the runtime: no -lcuda) ------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t inner, uint64_t rows,
+                uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) return fail(NB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {row_stride_bytes};
+    const cuuint32_t box[2] = {box_inner, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+    return NB200_OK;
+}
+
 
 }  // namespace nb200
 

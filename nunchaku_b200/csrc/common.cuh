@@ -2,6 +2,7 @@
 // 4-bit codes land on the same side of rounding boundaries), error plumbing.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -18,6 +19,9 @@ void set_last_error(const std::string &msg);
 int fail(int code, const std::string &msg);
 void count_launch(int n = 1);
 void reset_launch_count();
+// 2-D row-major tensor map: `inner` elements per row, box = box_inner x box_rows
+int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t inner, uint64_t rows,
+                uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz);
 
 #define NB200_CUDA_CHECK(expr)                                                                      \
     do {                                                                                            \

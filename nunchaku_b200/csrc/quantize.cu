@@ -290,7 +290,17 @@ int launch(const QParams &p, cudaStream_t stream) {
 }
 
 }  // namespace
+
+int quantize_v2_dispatch(const nb200_quantize_args &a, cudaStream_t stream);
+
 }  // namespace nb200
+
+extern "C" __attribute__((visibility("default"))) long long nb200_quantize_workspace_bytes(int Mp, int K) {
+    if (Mp <= 0 || K <= 0) return 0;
+    const long long row_blocks = Mp / 32;
+    const long long ks_max = (160 + row_blocks - 1) / row_blocks;
+    return ((row_blocks * 4 + 255) / 256) * 256 + ks_max * Mp * 32 * 4;
+}
 
 extern "C" __attribute__((visibility("default"))) int nb200_quantize_w4a4_act_fuse_lora(const nb200_quantize_args *a, void *stream_) {
     using namespace nb200;
@@ -304,11 +314,14 @@ extern "C" __attribute__((visibility("default"))) int nb200_quantize_w4a4_act_fu
     NB200_REQUIRE(a->dtype == NB200_FP16 || a->dtype == NB200_BF16, "dtype must be fp16 or bf16");
     NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->input) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->output) & 15) == 0,
                   "input/output must be 16-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!a->fuse_glu) return quantize_v2_dispatch(*a, stream);
     QParams p;
     p.x = a->input;
     p.q = static_cast<uint8_t *>(a->output);
     p.scales = a->oscales;
-    p.ld = a->lora_down;
+    // second half of the repacked factor: k-permuted fragments (nb200_repack_lora_down)
+    p.ld = static_cast<const uint8_t *>(a->lora_down) + static_cast<size_t>(a->K) * ((a->R + 31) / 32 * 32) * 2;
     p.lora = a->lora_act_out;
     p.smooth = a->smooth;
     p.M = a->M;
@@ -317,7 +330,6 @@ extern "C" __attribute__((visibility("default"))) int nb200_quantize_w4a4_act_fu
     p.R = a->R;
     p.Rp = (a->R + 31) / 32 * 32;
     p.x_stride = a->fuse_glu ? 2 * a->K : a->K;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const bool bf16 = a->dtype == NB200_BF16;
 #define NB200_Q_DISPATCH(HT)                                                         \
     if (a->fp4) {                                                                    \

@@ -1,0 +1,337 @@
+// Activation quantiser + low-rank down projection, TMA-fed version (the default for non-GLU inputs).
+//
+// Same contract as quantize.cu (reference quantize_w4a4_fuse_lora_kernel, gemm_w4a4.cuh:1097-1184).
+// v1 streamed rows straight into registers and was latency bound (16 % of HBM peak, ncu
+// profiles/r01_quantize.txt: 8 resident warps, 30 % issue active, loads serialised behind math).
+// v2 decouples memory from math:
+//   * one elected producer thread keeps a 16-deep ring of TMA tiles in flight per CTA
+//     (cp.async.bulk.tensor.2d, [32 rows x 64 k] = one quantisation group per row, 128B swizzle,
+//     rows >= M are zero-filled by the tensor map) -> 64 KB outstanding per SM without a register;
+//   * 8 consumer warps take the groups round-robin: ldmatrix.x4 A fragments + mma.sync.m16n8k16
+//     for x @ lora_down^T (fp32), then the per-row absmax / 4-bit rounding with the reference's exact
+//     instruction recipe, 8 lanes per row so a warp store covers 32 contiguous bytes per row;
+//   * optional split of K across CTAs (small M): per-split partial projections go to a workspace and
+//     the LAST CTA of a row block (atomic ticket) sums them in split order -> still deterministic.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace nb200 {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int kRows = 32;
+constexpr int kConsumers = 8;
+constexpr int kStages = 16;
+constexpr int kThreads = (kConsumers + 1) * 32;
+constexpr int kTileBytes = kRows * 128;
+
+struct Q2Params {
+    uint8_t *q;
+    void *scales;
+    const void *ld;  // [K/32][Rp/8][32 lanes][2 ksteps][2] u32 : mma.sync B fragments, true k order
+    float *lora;     // [Mp, R]
+    const void *smooth;
+    float *ws_partial;  // [KS][Mp][32] per rank chunk, or null when KS == 1
+    unsigned int *ws_ticket;  // [Mp / 32]
+    int M, Mp, K, R, Rp, KS;
+};
+
+struct alignas(1024) Q2Smem {
+    alignas(1024) uint8_t tile[kStages][kTileBytes];
+    float red[kConsumers][kRows][33];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    unsigned int is_last;
+};
+
+template <typename hT>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (HalfTraits<hT>::kIsBf16) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    } else {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+
+template <typename hT, bool FP4>
+__global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
+    using Tr = HalfTraits<hT>;
+    using T2 = typename Tr::T2;
+    extern __shared__ uint8_t smem_raw[];
+    Q2Smem &s = *reinterpret_cast<Q2Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rb = blockIdx.x;            // row block
+    const int ks = blockIdx.y;            // k split
+    const int row0 = rb * kRows;
+    const int G = p.K >> 6;
+    const int g_begin = static_cast<int>((static_cast<long long>(G) * ks) / p.KS);
+    const int g_end = static_cast<int>((static_cast<long long>(G) * (ks + 1)) / p.KS);
+    const int n_groups = g_end - g_begin;
+    const int n_chunks = p.Rp >> 5;
+    const int nt_total = p.Rp >> 3;
+
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&tm_x);
+        for (int i = 0; i < kStages; i++) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumers) {
+        // ============================ TMA producer ==============================================
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (int chunk = 0; chunk < n_chunks; chunk++) {
+                for (int i = 0; i < n_groups; i++, it++) {
+                    const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(&s.empty[st], ph ^ 1);
+                    mbar_expect_tx(&s.full[st], kTileBytes);
+                    tma_load_2d(s.tile[st], &tm_x, &s.full[st], (g_begin + i) * 64, row0);
+                }
+            }
+        }
+    } else {
+        // ============================ consumers ==================================================
+        const int gq = lane >> 2, t = lane & 3;   // mma fragment coordinates
+        const int r4 = lane >> 3, c = lane & 7;   // quantiser: row within 4, 16-byte chunk within the group
+        const hT *smooth = reinterpret_cast<const hT *>(p.smooth);
+        const uint4 *ldw = reinterpret_cast<const uint4 *>(p.ld);
+        uint32_t it_base = 0;
+        for (int chunk = 0; chunk < n_chunks; chunk++, it_base += n_groups) {
+            float acc[2][4][4];
+#pragma unroll
+            for (int m = 0; m < 2; m++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[m][j][e] = 0.f;
+
+            for (int i = warp; i < n_groups; i += kConsumers) {
+                const int g = g_begin + i;
+                const uint32_t it = it_base + i;
+                const uint32_t st = it % kStages, ph = (it / kStages) & 1;
+                // B fragments (L2 resident) and smoothing factors first: independent of the tile
+                uint4 bw[2][4];
+#pragma unroll
+                for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        bw[kb][j] = ldg_v4(ldw + (static_cast<size_t>(g * 2 + kb) * nt_total + chunk * 4 + j) * 32 + lane);
+                uint4 sm = make_uint4(0, 0, 0, 0);
+                if (chunk == 0 && smooth != nullptr) sm = ldg_v4(smooth + g * 64 + c * 8);
+
+                mbar_wait(&s.full[st], ph);
+                const uint32_t tile = smem_u32(s.tile[st]);
+
+                // ---- x @ lora_down^T on the un-smoothed tile (lora.cuh:243-353) ---------------------
+#pragma unroll
+                for (int m = 0; m < 2; m++) {
+#pragma unroll
+                    for (int kstep = 0; kstep < 4; kstep++) {
+                        const int r = m * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+                        const int ch = kstep * 2 + (lane >> 4);
+                        uint32_t a[4];
+                        ldmatrix_x4(tile + r * 128 + ((ch ^ (r & 7)) << 4), a);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 &b = bw[kstep >> 1][j];
+                            if (kstep & 1)
+                                mma16816<hT>(acc[m][j], a, b.z, b.w);
+                            else
+                                mma16816<hT>(acc[m][j], a, b.x, b.y);
+                        }
+                    }
+                }
+
+                // ---- smooth + quantise: 8 lanes per row, 4 rows per pass (gemm_w4a4.cuh:85-187,429-523) --
+                if (chunk == 0) {
+#pragma unroll 2
+                    for (int pass = 0; pass < kRows / 4; pass++) {
+                        const int r = pass * 4 + r4;
+                        const int m = row0 + r;
+                        const uint4 xv = *reinterpret_cast<const uint4 *>(s.tile[st] + r * 128 + ((c ^ (r & 7)) << 4));
+                        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                        const uint32_t sw[4] = {sm.x, sm.y, sm.z, sm.w};
+                        float xs[8];
+                        float amax = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            float2 a = Tr::to_float2(*reinterpret_cast<const T2 *>(&xw[e]));
+                            if (smooth != nullptr) {
+                                const float2 b = Tr::to_float2(*reinterpret_cast<const T2 *>(&sw[e]));
+                                a = Tr::to_float2(Tr::from_float2(make_float2(__fdividef(a.x, b.x), __fdividef(a.y, b.y))));
+                            }
+                            xs[2 * e] = a.x;
+                            xs[2 * e + 1] = a.y;
+                            amax = fmaxf(amax, fmaxf(fabsf(a.x), fabsf(a.y)));
+                        }
+                        uint8_t *qdst = p.q + static_cast<size_t>(m) * (p.K >> 1) + ((g * 64 + c * 8) >> 1);
+                        if constexpr (!FP4) {
+                            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                            const float s32 = amax * (1.0f / 7.0f);
+                            const float rs = rcp_approx_ftz(s32);
+                            if (c == 0) reinterpret_cast<hT *>(p.scales)[static_cast<size_t>(g) * p.Mp + m] = Tr::from_float(s32);
+                            int qv[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e++) qv[e] = cvt_rni(xs[e] * rs);
+                            *reinterpret_cast<uint32_t *>(qdst) = pack8_int4_b200<false>(qv);
+                        } else {
+                            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));   // 16-group = chunk pair
+                            const float sc = fminf(amax * (1.0f / 6.0f), 448.0f);
+                            const float rs = rcp_approx_ftz(sc);
+                            uint32_t w = 0;
+#pragma unroll
+                            for (int e = 0; e < 4; e++) w |= cvt_e2m1x2(xs[2 * e + 1] * rs, xs[2 * e] * rs) << (8 * e);
+                            *reinterpret_cast<uint32_t *>(qdst) = w;
+                            // scale bytes of the four 16-groups live in lanes c = 0, 2, 4, 6 -> gather in c == 0
+                            uint32_t sb = cvt_e4m3x2(0.f, sc) & 0xFFu;
+                            sb |= __shfl_down_sync(0xffffffffu, sb, 2) << 8;    // c: {0,2}  4: {4,6}
+                            sb |= __shfl_down_sync(0xffffffffu, sb, 4) << 16;   // c == 0: {0,2,4,6}
+                            if (c == 0) {
+                                uint8_t *sf = reinterpret_cast<uint8_t *>(p.scales) + (static_cast<size_t>(m >> 7) * G + g) * 512 +
+                                              (m & 31) * 16 + ((m & 127) >> 5) * 4;
+                                *reinterpret_cast<uint32_t *>(sf) = sb;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.empty[st]);
+            }
+
+            // ---- fixed-order reduction of the per-warp partial projections --------------------------
+#pragma unroll
+            for (int m = 0; m < 2; m++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    s.red[warp][m * 16 + gq][j * 8 + t * 2] = acc[m][j][0];
+                    s.red[warp][m * 16 + gq][j * 8 + t * 2 + 1] = acc[m][j][1];
+                    s.red[warp][m * 16 + gq + 8][j * 8 + t * 2] = acc[m][j][2];
+                    s.red[warp][m * 16 + gq + 8][j * 8 + t * 2 + 1] = acc[m][j][3];
+                }
+            named_bar_sync(1, kConsumers * 32);
+            const int ct = threadIdx.x;  // 0..255
+            float sum[kRows * 32 / (kConsumers * 32)];
+#pragma unroll
+            for (int u = 0; u < kRows * 32 / (kConsumers * 32); u++) {
+                const int idx = ct + u * kConsumers * 32;
+                const int rr = idx >> 5, cc = idx & 31;
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < kConsumers; w++) v += s.red[w][rr][cc];
+                sum[u] = v;
+            }
+            if (p.KS == 1) {
+#pragma unroll
+                for (int u = 0; u < kRows * 32 / (kConsumers * 32); u++) {
+                    const int idx = ct + u * kConsumers * 32;
+                    const int rr = idx >> 5, rank = chunk * 32 + (idx & 31);
+                    if (rank < p.R) p.lora[static_cast<size_t>(row0 + rr) * p.R + rank] = sum[u];
+                }
+            } else {
+                // partial of this k split -> workspace; the last split to finish sums all of them in split order
+                float *mine = p.ws_partial + (static_cast<size_t>(ks) * p.Mp + row0) * 32;
+#pragma unroll
+                for (int u = 0; u < kRows * 32 / (kConsumers * 32); u++) mine[ct + u * kConsumers * 32] = sum[u];
+                __threadfence();
+                named_bar_sync(1, kConsumers * 32);
+                if (ct == 0) {
+                    const unsigned int ticket = atomicAdd(&p.ws_ticket[rb], 1u);
+                    s.is_last = (ticket == static_cast<unsigned int>(p.KS) - 1u) ? 1u : 0u;
+                    if (s.is_last) p.ws_ticket[rb] = 0;  // self-cleaning for the next chunk / call
+                }
+                named_bar_sync(1, kConsumers * 32);
+                if (s.is_last) {
+                    __threadfence();
+#pragma unroll
+                    for (int u = 0; u < kRows * 32 / (kConsumers * 32); u++) {
+                        const int idx = ct + u * kConsumers * 32;
+                        const int rr = idx >> 5, rank = chunk * 32 + (idx & 31);
+                        float v = 0.f;
+                        for (int k2 = 0; k2 < p.KS; k2++)
+                            v += __ldcg(p.ws_partial + (static_cast<size_t>(k2) * p.Mp + row0) * 32 + idx);
+                        if (rank < p.R) p.lora[static_cast<size_t>(row0 + rr) * p.R + rank] = v;
+                    }
+                }
+            }
+            named_bar_sync(1, kConsumers * 32);
+        }
+    }
+}
+
+}  // namespace
+
+template <typename hT, bool FP4>
+static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
+    CUtensorMap tm_x;
+    const CUtensorMapDataType dt = HalfTraits<hT>::kIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    int rc = make_map_2d(&tm_x, dt, a.input, a.K, a.M, static_cast<uint64_t>(a.K) * 2, 64, kRows, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    Q2Params p;
+    p.q = static_cast<uint8_t *>(a.output);
+    p.scales = a.oscales;
+    p.ld = a.lora_down;
+    p.lora = a.lora_act_out;
+    p.smooth = a.smooth;
+    p.M = a.M;
+    p.Mp = a.Mp;
+    p.K = a.K;
+    p.R = a.R;
+    p.Rp = (a.R + 31) / 32 * 32;
+    // split K across CTAs only when the row blocks alone would leave most SMs idle
+    const int row_blocks = a.Mp / kRows;
+    const int G = a.K / 64;
+    int ks = 1;
+    if (a.workspace != nullptr && row_blocks < 96 && p.Rp == 32) {
+        ks = (160 + row_blocks - 1) / row_blocks;
+        if (ks > G / kConsumers) ks = G / kConsumers;
+        if (ks < 1) ks = 1;
+        const size_t need = static_cast<size_t>(ks) * a.Mp * 32 * sizeof(float) + static_cast<size_t>(row_blocks) * sizeof(unsigned int);
+        if (need > static_cast<size_t>(a.workspace_bytes)) ks = 1;
+    }
+    p.KS = ks;
+    p.ws_ticket = static_cast<unsigned int *>(a.workspace);
+    p.ws_partial = a.workspace ? reinterpret_cast<float *>(static_cast<uint8_t *>(a.workspace) + ((static_cast<size_t>(row_blocks) * 4 + 255) & ~static_cast<size_t>(255))) : nullptr;
+    const size_t smem = sizeof(Q2Smem) + 1024;
+    auto kern = quantize_v2_kernel<hT, FP4>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_set = true;
+    }
+    kern<<<dim3(row_blocks, ks), kThreads, smem, stream>>>(tm_x, p);
+    count_launch();
+    NB200_CUDA_CHECK(cudaGetLastError());
+    return NB200_OK;
+}
+
+int quantize_v2_dispatch(const nb200_quantize_args &a, cudaStream_t stream) {
+    const bool bf16 = a.dtype == NB200_BF16;
+    if (bf16) return a.fp4 ? launch_q2<__nv_bfloat16, true>(a, stream) : launch_q2<__nv_bfloat16, false>(a, stream);
+    return a.fp4 ? launch_q2<__half, true>(a, stream) : launch_q2<__half, false>(a, stream);
+}
+
+}  // namespace nb200

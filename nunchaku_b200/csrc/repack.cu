@@ -129,24 +129,28 @@ __global__ void repack_lora_up_kernel(const hT *__restrict__ src, hT *__restrict
 
 // dst [K/32][Rp/8][lane = gq*4 + t][8]: element e of lane (gq, t) = Ld[rank 8j + gq][k = kb*32 + 8t + e]
 // (B fragments of the k-permuted mma.sync in quantize.cu)
+// second half additionally: the TMA kernel (quantize_v2.cu) feeds ldmatrix fragments in true k order:
+// first half dst [K/32][Rp/8][lane][ks2][b][e] = Ld[8j + gq][kb*32 + 16*ks2 + 8*b + 2*t + e]
 template <typename hT>
 __global__ void repack_lora_down_kernel(const hT *__restrict__ src, hT *__restrict__ dst, int K, int R, int Rp) {
     const size_t total = static_cast<size_t>(K) * Rp;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    for (size_t i2 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i2 < 2 * total;
+         i2 += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const bool permuted = i2 >= total;
+        const size_t i = permuted ? i2 - total : i2;
         const int e8 = static_cast<int>(i & 7), lane = static_cast<int>((i >> 3) & 31);
         const size_t blk = i >> 8;  // kb * (Rp/8) + j
         const int kb = static_cast<int>(blk / (Rp >> 3)), j = static_cast<int>(blk % (Rp >> 3));
         const int gq = lane >> 2, t = lane & 3;
         const int r = j * 8 + gq;
-        const int k = kb * 32 + t * 8 + e8;
+        const int k = permuted ? kb * 32 + t * 8 + e8 : kb * 32 + (e8 >> 2) * 16 + ((e8 >> 1) & 1) * 8 + t * 2 + (e8 & 1);
         hT v = HalfTraits<hT>::from_float(0.f);
         if (r < R) {
             const int u = r >> 4, h = (r >> 3) & 1, g = r & 7;
             const int ii = k >> 4, c = (k >> 3) & 1, tt = (k >> 1) & 3, e = k & 1;
             v = src[ref_lowrank_index(ii, u, g, tt, h, c, e, R)];
         }
-        dst[i] = v;
+        dst[i2] = v;
     }
 }
 
@@ -251,7 +255,7 @@ extern "C" __attribute__((visibility("default"))) int nb200_repack_lora_down(con
     NB200_REQUIRE(K % 32 == 0 && R % 16 == 0 && R > 0, "K % 32 == 0, R % 16 == 0, R > 0 required");
     NB200_REQUIRE(dtype == NB200_FP16 || dtype == NB200_BF16, "dtype must be fp16 or bf16");
     const int Rp = (R + 31) / 32 * 32;
-    const size_t total = static_cast<size_t>(K) * Rp;
+    const size_t total = 2 * static_cast<size_t>(K) * Rp;
     if (dtype == NB200_BF16)
         repack_lora_down_kernel<__nv_bfloat16><<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16 *>(src), static_cast<__nv_bfloat16 *>(dst), K, R, Rp);

@@ -71,6 +71,23 @@ def svdq_quantize_w4a4_act_fuse_lora_cuda(
     args.M, args.Mp, args.K, args.R = batch_size, batch_size_pad, channels, rank
     args.dtype = torch_dtype_code(input.dtype)
     args.fuse_glu, args.fp4 = int(fuse_glu), int(fp4)
+    ws = _workspace(batch_size_pad, channels, input.device)
+    args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
     check(lib.nb200_quantize_w4a4_act_fuse_lora(ctypes.byref(args), torch.cuda.current_stream().cuda_stream),
           "quantize_w4a4_act_fuse_lora")
     return output, oscales, lora_act_out
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(Mp: int, K: int, device) -> torch.Tensor:
+    """Zero-initialised scratch for the small-M split-K path (kernel leaves it clean); one per
+    (device, stream) and grown on demand -- allocate before CUDA-graph capture by warming up."""
+    need = int(lib.nb200_quantize_workspace_bytes(Mp, K))
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws

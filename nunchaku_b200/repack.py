@@ -133,7 +133,7 @@ def lora_down(ld: torch.Tensor) -> torch.Tensor:
         return hit
     K, R = ld.shape
     Rp = (R + 31) // 32 * 32
-    out = torch.empty(K * Rp, dtype=ld.dtype, device=ld.device)
+    out = torch.empty(2 * K * Rp, dtype=ld.dtype, device=ld.device)
     check(lib.nb200_repack_lora_down(ld.data_ptr(), out.data_ptr(), K, R, torch_dtype_code(ld.dtype), _stream()),
           "repack_lora_down")
     return _store("lora_down", ld, sig, out)

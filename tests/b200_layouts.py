@@ -81,10 +81,13 @@ def lora_up_blocks(lu: torch.Tensor, cscale: torch.Tensor | None = None) -> torc
 
 
 def lora_down_frags(ld: torch.Tensor) -> torch.Tensor:
-    """logical [R, K] -> [K/32][Rp/8][lane = gq*4+t][8] with element e = Ld[8j+gq][kb*32+8t+e]."""
+    """logical [R, K] -> two fragment layouts back to back, each [K/32][Rp/8][lane = gq*4+t][8]:
+      first  (TMA kernel, true k order): element (ks2, b, e) = Ld[8j+gq][kb*32 + 16*ks2 + 8*b + 2*t + e]
+      second (register-streaming kernel): element e          = Ld[8j+gq][kb*32 + 8*t + e]"""
     R, K = ld.shape
     Rp = (R + 31) // 32 * 32
     v = torch.zeros(Rp, K, dtype=ld.dtype, device=ld.device)
     v[:R] = ld
-    v = v.view(Rp // 8, 8, K // 32, 4, 8).permute(2, 0, 1, 3, 4).contiguous()  # kb, j, gq, t, e
-    return v.reshape(-1)
+    perm = v.view(Rp // 8, 8, K // 32, 4, 8).permute(2, 0, 1, 3, 4).contiguous()  # kb, j, gq, t, e
+    true = v.view(Rp // 8, 8, K // 32, 2, 2, 4, 2).permute(2, 0, 1, 5, 3, 4, 6).contiguous()  # kb, j, gq, t, ks2, b, e
+    return torch.cat([true.reshape(-1), perm.reshape(-1)])

@@ -42,10 +42,10 @@ def test_abi_version_and_argument_validation_without_gpu():
 
 def test_struct_layout_matches_header_sizes():
     """ctypes mirrors of nb200_quantize_args / nb200_gemm_args: field order is taken from the
-    header; sizes are what a C compiler produces for it (6*8 + 7*4 -> 80; 17*8 + 11*4 + 64*4 + 2*4 -> 448)."""
+    header; sizes are what a C compiler produces for it (6*8 + 7*4 + pad + 8 + 8 -> 96; 17*8 + 11*4 + 64*4 + 2*4 -> 448)."""
     import ctypes
 
     from nunchaku_b200._C import GemmArgs, QuantizeArgs
 
-    assert ctypes.sizeof(QuantizeArgs) == 80
+    assert ctypes.sizeof(QuantizeArgs) == 96
     assert ctypes.sizeof(GemmArgs) == 17 * 8 + 11 * 4 + 64 * 4 + 2 * 4 + 4  # + tail padding to 8
