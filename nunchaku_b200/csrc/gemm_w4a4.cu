@@ -25,6 +25,9 @@
 #include "ptx.cuh"
 
 namespace nb200 {
+
+int gemm_w4a4_2cta_dispatch(const nb200_gemm_args &a, cudaStream_t stream);
+
 namespace {
 
 using namespace ptx;
@@ -771,11 +774,15 @@ template <bool FP4, typename hT>
 int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
     if (a.qout != nullptr) return launch<FP4, hT, 128, EPI_QUANT>(a, stream);
     if (a.rotary_emb != nullptr) return launch<FP4, hT, 128, EPI_ROPE>(a, stream);
+    if (a.block_n == 512) {  // CTA pairs (cta_group::2), 256 x 256 tiles
+        if (a.N % 256 != 0) return fail(NB200_ERR_INVALID_ARGUMENT, "the CTA-pair kernel needs N % 256 == 0");
+        return gemm_w4a4_2cta_dispatch(a, stream);
+    }
     int bn = a.block_n;
     if (bn == 0) bn = (a.N % 256 == 0 && (a.Mp / BM) * (a.N / 256) >= 96) ? 256 : 128;
     if (bn == 256 && a.N % 256 == 0) return launch<FP4, hT, 256, EPI_DEFAULT>(a, stream);
     if (bn == 128) return launch<FP4, hT, 128, EPI_DEFAULT>(a, stream);
-    return fail(NB200_ERR_INVALID_ARGUMENT, "block_n must be 0, 128 or 256 and divide N");
+    return fail(NB200_ERR_INVALID_ARGUMENT, "block_n must be 0, 128, 256 (single CTA) or 512 (CTA pair) and divide N");
 }
 
 }  // namespace

@@ -82,7 +82,7 @@ def _assert_parity(out, y_exact, y_ref, hT, name):
     assert e_exact <= ref_noise + tol_exact, msg
 
 
-@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("block_n", [128, 256, 512])   # 512 = CTA-pair kernel (cta_group::2)
 @pytest.mark.parametrize("fp4", [False, True])
 @pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
 def test_gemm_small(fp4, hT, block_n):
@@ -112,15 +112,16 @@ def test_gemm_main_only_then_pieces(fp4):
                        f"pieces fp4={fp4} bias={with_bias} lora={with_lora}")
 
 
+@pytest.mark.parametrize("block_n", [0, 512])
 @pytest.mark.parametrize("fp4", [False, True])
-def test_gemm_rank_variants_and_lora_scales(fp4):
+def test_gemm_rank_variants_and_lora_scales(fp4, block_n):
     hT = torch.bfloat16
     N, K, M = 256, 256, 256
     for R, scales in [(16, None), (48, [0.5, 2.0, 1.0]), (64, [1.0, 0.0, 1.0, -1.0])]:
         layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=31 + R)
         x = O.make_activations(M, K, hT, seed=32, smooth=layer.smooth)
         qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=fp4)
-        out = _gemm(layer, qa, ref_layout_params(layer), M, lora_scales=scales)
+        out = _gemm(layer, qa, ref_layout_params(layer), M, lora_scales=scales, block_n=block_n)
         _assert_parity(out, _oracle(layer, qa, M, "exact", lora_scales=scales),
                        _oracle(layer, qa, M, "ref", lora_scales=scales), hT, f"rank {R} fp4={fp4}")
 
@@ -188,8 +189,9 @@ def test_linear_module_3072(precision, hT):
     assert e_ref <= 1.5e-2 and e_ex <= 1e-2, msg
 
 
+@pytest.mark.parametrize("block_n", [0, 512])
 @pytest.mark.parametrize("fp4", [False, True])
-def test_gemm_full_size_vs_fp32_on_gpu(fp4):
+def test_gemm_full_size_vs_fp32_on_gpu(fp4, block_n):
     """M=4352 (FLUX.1-schnell single stream), 3072x3072 r=32: too big for the CPU oracle in
     seconds, so evaluate the SAME quantised operands in fp32 with torch on the GPU
     (size-independent property: the kernel is linear in the dequantised operands)."""
@@ -213,7 +215,7 @@ def test_gemm_full_size_vs_fp32_on_gpu(fp4):
         w = (layer.qw.to(dev).float().view(N, K // 64, 64) * layer.wscales.to(dev).float().unsqueeze(-1)).view(N, K)
     la = torch.randn(Mp, R, generator=g)
     qa = O.QuantizedAct(q=qa_q, scales=qa_s, lora_act=la, M=M)
-    out = _gemm(layer, qa, params, M)
+    out = _gemm(layer, qa, params, M, block_n=block_n)
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
@@ -226,3 +228,22 @@ def test_gemm_full_size_vs_fp32_on_gpu(fp4):
         torch.backends.cuda.matmul.allow_tf32 = old
     e = O.rel_fro(out.cpu(), y.cpu()[:M])
     assert e <= 3e-3, f"full size fp4={fp4}: rel_fro {e:.3e}\n" + diag("full", out, y[:M])
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+def test_gemm_cta_pair_many_tiles_and_k_tail(fp4):
+    """CTA-pair kernel over several pair tiles (persistent loop, accumulator/stage phase wrap) with
+    a K that is not a multiple of 256 (FP4 k tail) and a ragged M."""
+    hT = torch.bfloat16
+    N, K, R, M = 768, 640, 32, 900
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=81)
+    x = O.make_activations(M, K, hT, seed=82, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=fp4)
+    from nunchaku_b200.ops import gemm as G
+
+    G.NUM_SMS_OVERRIDE = 4      # 2 pairs for 12 pair tiles -> 6 tiles per pair
+    try:
+        out = _gemm(layer, qa, ref_layout_params(layer), M, block_n=512)
+    finally:
+        G.NUM_SMS_OVERRIDE = 0
+    _assert_parity(out, _oracle(layer, qa, M, "exact"), _oracle(layer, qa, M, "ref"), hT, f"cta-pair many tiles fp4={fp4}")

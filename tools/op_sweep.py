@@ -57,7 +57,7 @@ def main():
     ap.add_argument("--iters", type=int, default=15)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--shapes", default="flux")
-    ap.add_argument("--bn", default="0,128,256")
+    ap.add_argument("--bn", default="0,128,256,512")
     args = ap.parse_args()
     from nunchaku_b200.ops import gemm as G
 
@@ -87,7 +87,7 @@ def main():
             row = {"precision": prec, "M": M, "K": K, "N": N, "quant_us": qt, "quant_min_us": qmin, "quant_GBs": qbytes / qt / 1e3,
                    "quant_frac_hbm": qbytes / qt / 1e3 / hbm}
             for bn in [int(b) for b in args.bn.split(",")]:
-                if bn and N % bn:
+                if bn and N % min(bn, 256):
                     continue
                 G.BLOCK_N_OVERRIDE = bn
                 try:
