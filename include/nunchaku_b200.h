@@ -156,8 +156,9 @@ typedef struct nb200_gemm_args {
     int mid_act;           /* nb200_act; GELU is implied when qout != NULL                 */
     float lora_scales[NB200_MAX_LORA_SCALES];
     /* tuning (0 = auto) */
-    int block_n;
+    int block_n;           /* 128 / 256: single-CTA tiles; 512: CTA-pair (cta_group::2) 256x256 tiles      */
     int num_sms;
+    void *prof;            /* optional device buffer, 16 x int64 per CTA: barrier-wait cycle counters  */
 } nb200_gemm_args;
 
 int nb200_gemm_w4a4(const nb200_gemm_args *args, void *stream);

@@ -72,6 +72,7 @@ class GemmArgs(ctypes.Structure):
         ("lora_scales", c_float * NB200_MAX_LORA_SCALES),
         ("block_n", c_int),
         ("num_sms", c_int),
+        ("prof", c_void_p),
     ]
 
 

@@ -64,6 +64,7 @@ struct GemmParams {
     // EPI_ROPE
     const void *norm_q, *norm_k;  // hT [128]
     const float *rotary;          // reference pack_rotemb layout [Mp][128]
+    long long *prof;              // optional [grid][16] cycle counters (tools/gemm_prof.py)
     float lora_scales[NB200_MAX_LORA_SCALES];
 };
 
@@ -83,7 +84,13 @@ struct Cfg {
     static constexpr int kTmemSfa = kNumAcc * BN;
     static constexpr int kTmemSfb = kTmemSfa + kSfaCols;
     static constexpr int kTmemLd = FP4 ? kTmemSfb + kSfbCols : kNumAcc * BN;  // EPI_QUANT: D2 [128 x Rdp]
-    static constexpr int kThreads = FP4 ? 256 : 512;
+    // FP4 mainloops are 4x shorter than INT4 ones, so the epilogue is the bottleneck (measured: the fused
+    // fc1 epilogue needs ~5k issue cycles per 128x128 tile against a 3k-cycle mainloop): two half-groups of
+    // 4 warps drain the two column halves of a tile concurrently.  INT4 keeps one group (its 8 converter
+    // warps already fill the register file).
+    static constexpr int kEpiGroups = FP4 ? 2 : 1;
+    static constexpr int kEpiThreads = 128 * kEpiGroups;
+    static constexpr int kThreads = FP4 ? (4 + 4 * kEpiGroups) * 32 : 512;
     static_assert(!FP4 || kTmemSfb + kSfbCols <= 512, "TMEM budget");
     static_assert(kNumAcc * BN <= 512, "TMEM budget");
     static_assert(EPI != EPI_QUANT || (BN == 128 && kTmemLd + kMaxRdp <= 512), "fused quantise epilogue uses 128-wide tiles");
@@ -111,6 +118,7 @@ struct alignas(1024) Smem {
     alignas(1024) uint8_t ld_b[EPI == EPI_QUANT ? (BN / 64) * kMaxRdp * 128 : 16];
     float bias[BN];
     float cscale[BN];
+    float ropesum[2][BM];  // EPI_ROPE with two epilogue groups: per-row partial sums of squares
     float aux[256];  // EPI_QUANT: next layer's smooth factors of this tile; EPI_ROPE: RMSNorm weights (q | k)
     uint64_t full[C::kStages];
     uint64_t empty[C::kStages];
@@ -127,6 +135,14 @@ struct alignas(1024) Smem {
     uint64_t d2_full;
     uint32_t tmem_base;
 };
+
+// cycle accounting of the barrier waits (written out only when p.prof != nullptr)
+#define NB200_TIMED(acc, stmt)            \
+    do {                                  \
+        const long long _t0 = clock64();  \
+        stmt;                             \
+        (acc) += clock64() - _t0;         \
+    } while (0)
 
 struct PipeState {
     uint32_t idx = 0, phase = 0;
@@ -185,6 +201,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     S &s = *reinterpret_cast<S *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
+    const long long t_kernel0 = clock64();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k64_total = p.K >> 6;
@@ -201,24 +218,24 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < C::kStages; i++) {
             mbar_init(&s.full[i], 1);
-            mbar_init(&s.empty[i], FP4 ? 1 : kNumConvThreads);
+            mbar_init(&s.empty[i], FP4 ? 1 : kNumConvThreads / 32);
         }
         for (int i = 0; i < C::kConvStages; i++) {
-            mbar_init(&s.cfull[i], kNumConvThreads);
+            mbar_init(&s.cfull[i], kNumConvThreads / 32);
             mbar_init(&s.cempty[i], 1);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&s.tmem_full[i], 1);
-            mbar_init(&s.tmem_empty[i], kNumEpiThreads);
+            mbar_init(&s.tmem_empty[i], C::kEpiThreads);
         }
         mbar_init(&s.lora_b_full, 1);
-        mbar_init(&s.lora_a_full, kNumEpiThreads);
+        mbar_init(&s.lora_a_full, C::kEpiThreads);
         mbar_init(&s.lora_empty, 1);
         mbar_init(&s.ld_b_full, 1);
-        mbar_init(&s.ld_b_empty, 1);
+        mbar_init(&s.ld_b_empty, C::kEpiGroups);
         mbar_init(&s.stage_mma_done[0], 1);
         mbar_init(&s.stage_mma_done[1], 1);
-        mbar_init(&s.d2_full, 1);
+        mbar_init(&s.d2_full, C::kEpiGroups);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(&s.tmem_base);
@@ -226,6 +243,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = s.tmem_base;
+    const long long t_setup = clock64() - t_kernel0;
 
     if (warp == 0) {
         // =================================== TMA producer =======================================
@@ -233,6 +251,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             PipeState st;
             uint32_t lora_phase = 0;
             uint32_t ld_phase = 0;
+            long long t_empty = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int mb = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
                 const int m0 = mb * BM, n0 = nb * BN;
@@ -247,7 +266,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     }
                 }
                 for (int kb = 0; kb < num_kblocks; kb++) {
-                    mbar_wait(&s.empty[st.idx], st.phase ^ 1);
+                    NB200_TIMED(t_empty, mbar_wait(&s.empty[st.idx], st.phase ^ 1));
                     if constexpr (FP4) {
                         const int nj = min(4, k64_total - 4 * kb);
                         const uint32_t sf_bytes = nj * 512;
@@ -281,6 +300,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     lora_phase ^= 1;
                 }
             }
+            if (p.prof) p.prof[blockIdx.x * 16 + 0] = t_empty;
         }
     } else if (warp == 1) {
         // ==================================== MMA issuer ========================================
@@ -289,16 +309,19 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             uint32_t lora_phase = 0;
             uint32_t acc_phase[2] = {0, 0};
             int it = 0;
+            long long t_tmem_empty = 0, t_full = 0, t_lora = 0, t_first = 0;
+            const long long t_mma0 = clock64();
             constexpr uint32_t idesc_main = FP4 ? make_idesc_nvf4(BM, BN) : make_idesc_f16(Tr::kIsBf16, BM, BN);
             constexpr uint32_t idesc_lora = make_idesc_f16(Tr::kIsBf16, BM, BN);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
                 const int acc = it % C::kNumAcc;
-                mbar_wait(&s.tmem_empty[acc], acc_phase[acc] ^ 1);
+                NB200_TIMED(t_tmem_empty, mbar_wait(&s.tmem_empty[acc], acc_phase[acc] ^ 1));
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     if constexpr (FP4) {
-                        mbar_wait(&s.full[st.idx], st.phase);
+                        NB200_TIMED(t_full, mbar_wait(&s.full[st.idx], st.phase));
+                        if (t_first == 0) t_first = clock64() - t_mma0;
                         tc_fence_after_sync();
                         const int nj = min(4, k64_total - 4 * kb);
                         for (int j = 0; j < nj; j++) {
@@ -318,7 +341,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         tc_commit(&s.empty[st.idx]);
                         st.advance(C::kStages);
                     } else {
-                        mbar_wait(&s.cfull[st.idx], st.phase);
+                        NB200_TIMED(t_full, mbar_wait(&s.cfull[st.idx], st.phase));
+                        if (t_first == 0) t_first = clock64() - t_mma0;
                         tc_fence_after_sync();
                         const uint32_t a_addr = smem_u32(s.a_cv[st.idx]), b_addr = smem_u32(s.b_cv[st.idx]);
 #pragma unroll
@@ -330,8 +354,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     }
                 }
                 for (int c = 0; c < lora_chunks; c++) {
-                    mbar_wait(&s.lora_b_full, lora_phase);
-                    mbar_wait(&s.lora_a_full, lora_phase);
+                    NB200_TIMED(t_lora, mbar_wait(&s.lora_b_full, lora_phase));
+                    NB200_TIMED(t_lora, mbar_wait(&s.lora_a_full, lora_phase));
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem_u32(s.lora_a), b_addr = smem_u32(s.lora_b);
 #pragma unroll
@@ -344,35 +368,49 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 tc_commit(&s.tmem_full[acc]);
                 acc_phase[acc] ^= 1;
             }
+            if (p.prof) {
+                p.prof[blockIdx.x * 16 + 1] = t_tmem_empty;
+                p.prof[blockIdx.x * 16 + 2] = t_full;
+                p.prof[blockIdx.x * 16 + 3] = t_lora;
+                p.prof[blockIdx.x * 16 + 10] = clock64() - t_mma0;
+                p.prof[blockIdx.x * 16 + 13] = t_first;
+            }
         }
-    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4 * C::kEpiGroups) {
         // ===================================== epilogue ==========================================
-        const int q = warp - kEpiWarp0;        // TMEM lane quadrant
-        const int et = threadIdx.x - kEpiWarp0 * 32;
+        constexpr int H = C::kEpiGroups;       // half-groups of 4 warps; group h owns column chunks [h*CH/H, (h+1)*CH/H)
+        constexpr int CH = BN / 64;
+        const int h = (warp - kEpiWarp0) >> 2;
+        const int q = warp & 3;                // TMEM lane quadrant (hardware: warp id % 4)
+        const int et = threadIdx.x - (kEpiWarp0 + 4 * h) * 32;   // thread within the group
+        const int eta = threadIdx.x - kEpiWarp0 * 32;            // thread within all epilogue warps
         const int row = q * 32 + lane;         // row inside the tile
         uint32_t lora_phase = 0;
         uint32_t acc_phase[2] = {0, 0};
         int it = 0;
         uint32_t store_count = 0;
+        long long t_tmem_full = 0, t_pre = 0;
+        const long long t_epi0 = clock64();
         [[maybe_unused]] uint32_t ld_phase = 0, d2_phase = 0;
         [[maybe_unused]] uint32_t smd_phase[2] = {0, 0};
         if constexpr (EPI == EPI_ROPE) {
-            for (int i = et; i < 256; i += kNumEpiThreads)
+            for (int i = eta; i < 256; i += C::kEpiThreads)
                 s.aux[i] = Tr::to_float(reinterpret_cast<const hT *>(i < 128 ? p.norm_q : p.norm_k)[i & 127]);
         }
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
             const int mb = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
             const int m0 = mb * BM, n0 = nb * BN;
             const int acc = it % C::kNumAcc;
+            const long long t_tile0 = clock64();
 
             // per-tile channel vectors
-            named_bar_sync(1, kNumEpiThreads);
-            for (int i = et; i < BN; i += kNumEpiThreads) {
+            named_bar_sync(1, C::kEpiThreads);
+            for (int i = eta; i < BN; i += C::kEpiThreads) {
                 s.bias[i] = p.bias != nullptr ? p.bias[n0 + i] : 0.f;
                 s.cscale[i] = p.cscale != nullptr ? p.cscale[n0 + i] : 1.f;
                 if constexpr (EPI == EPI_QUANT) s.aux[i] = Tr::to_float(reinterpret_cast<const hT *>(p.smooth_next)[n0 + i]);
             }
-            named_bar_sync(1, kNumEpiThreads);
+            named_bar_sync(1, C::kEpiThreads);
 
             // low-rank activations: fp32 -> * lora_scale -> hT  (lora.cuh:145-151), one row per thread
             for (int c = 0; c < lora_chunks; c++) {
@@ -380,7 +418,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 const float *src = p.lora_act + static_cast<size_t>(m0 + row) * p.R + c * kLoraChunk;
                 uint8_t *dst = s.lora_a + (row >> 3) * 512 + (row & 7) * 16;
 #pragma unroll
-                for (int o = 0; o < 4; o++) {  // rank octet
+                for (int oo = 0; oo < 4 / H; oo++) {  // rank octets of this group
+                    const int o = h * (4 / H) + oo;
                     const int r0 = c * kLoraChunk + o * 8;
                     uint32_t w[4] = {0, 0, 0, 0};
                     if (r0 < p.R) {
@@ -403,7 +442,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 lora_phase ^= 1;
             }
 
-            mbar_wait(&s.tmem_full[acc], acc_phase[acc]);
+            t_pre += clock64() - t_tile0;
+            NB200_TIMED(t_tmem_full, mbar_wait(&s.tmem_full[acc], acc_phase[acc]));
             acc_phase[acc] ^= 1;
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -419,7 +459,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 if (do_rope) {
                     float sumsq = 0.f;
 #pragma unroll 1
-                    for (int c32 = 0; c32 < 4; c32++) {
+                    for (int cc = 0; cc < 4 / H; cc++) {
+                        const int c32 = h * (4 / H) + cc;
                         uint32_t v[32];
                         tmem_ld_32x32b_x32(taddr + c32 * 32, v);
                         tmem_ld_wait();
@@ -431,6 +472,11 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                             sumsq = fmaf(r.x, r.x, sumsq);
                             sumsq = fmaf(r.y, r.y, sumsq);
                         }
+                    }
+                    if constexpr (H == 2) {  // each group saw 64 of the head's 128 columns
+                        s.ropesum[h][row] = sumsq;
+                        named_bar_sync(1, C::kEpiThreads);
+                        sumsq = s.ropesum[0][row] + s.ropesum[1][row];
                     }
                     rope_coef = rsqrt_approx_ftz(sumsq / 128.f + 1e-6f);
                     normw = s.aux + part * 128;
@@ -448,21 +494,28 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             }
 
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 64; ch++) {
+            for (int cc = 0; cc < CH / H; cc++) {
+                const int ch = h * (CH / H) + cc;
                 uint32_t v0[32], v1[32];
                 tmem_ld_32x32b_x32(taddr + ch * 64, v0);
                 tmem_ld_32x32b_x32(taddr + ch * 64 + 32, v1);
                 tmem_ld_wait();
-                if (ch == BN / 64 - 1) {
+                if (cc == CH / H - 1) {
                     tc_fence_before_sync();
                     mbar_arrive(&s.tmem_empty[acc]);
                 }
-                const int buf = store_count & 1;
-                if (et == 0) bulk_wait_group_read<1>();
+                // staging buffer: one group -> two buffers alternate; two groups -> one buffer each
+                const int buf = H == 2 ? h : (store_count & 1);
+                if (et == 0) {
+                    if constexpr (H == 2)
+                        bulk_wait_group_read<0>();
+                    else
+                        bulk_wait_group_read<1>();
+                }
                 if constexpr (EPI == EPI_QUANT) {
                     if (p.R_down > 0) mbar_wait(&s.stage_mma_done[buf], smd_phase[buf] ^ 1);
                 }
-                named_bar_sync(2, kNumEpiThreads);
+                named_bar_sync(2 + 2 * h, kNumEpiThreads);
                 uint8_t *srow = s.out_stage[buf] + row * 128;
                 [[maybe_unused]] uint32_t gw[32];  // EPI_QUANT: the 64 hT values of this row/chunk
 #pragma unroll
@@ -515,7 +568,12 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     *reinterpret_cast<uint4 *>(srow + ((c8 ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(3, kNumEpiThreads);
+                named_bar_sync(3 + 2 * h, kNumEpiThreads);
+                if constexpr (EPI == EPI_QUANT && H == 2) {
+                    // the second group's down-projection MMAs accumulate onto the first group's (accumulate = 0):
+                    // issue them in order.  Named barrier 6: group 0's issuing warp arrives after issuing.
+                    if (p.R_down > 0 && h == 1 && q == 0) asm volatile("bar.sync 6, 64;" ::: "memory");
+                }
                 if (et == 0) {
                     if (EPI != EPI_QUANT || p.out != nullptr) {
                         tma_store_2d(&tm_out, s.out_stage[buf], n0 + ch * 64, m0);
@@ -536,6 +594,9 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                             tc_commit(&s.stage_mma_done[buf]);
                         }
                     }
+                }
+                if constexpr (EPI == EPI_QUANT && H == 2) {
+                    if (p.R_down > 0 && h == 0 && q == 0) asm volatile("bar.arrive 6, 64;" ::: "memory");
                 }
                 if constexpr (EPI == EPI_QUANT) {
                     smd_phase[buf] ^= 1;
@@ -625,7 +686,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     d2_phase ^= 1;
                     tc_fence_after_sync();
                     float *dst = p.lora_act_out + static_cast<size_t>(m0 + row) * p.R_down;
-                    for (int c16 = 0; c16 * 16 < p.Rdp; c16++) {
+                    // two groups: each adds half of the 16-rank column blocks
+                    for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
                         uint32_t d2[16];
                         tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kTmemLd + c16 * 16, d2);
                         tmem_ld_wait();
@@ -638,11 +700,17 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             }
         }
         if (et == 0) bulk_wait_group<0>();
+        if (p.prof && eta == 0) {
+            p.prof[blockIdx.x * 16 + 4] = t_tmem_full;
+            p.prof[blockIdx.x * 16 + 5] = clock64() - t_epi0;
+            p.prof[blockIdx.x * 16 + 11] = t_pre;
+        }
     } else if (!FP4 && warp >= kConvWarp0) {
         // ============================ INT4 -> hT converter warps ===================================
         if constexpr (!FP4) {
             const int ct = threadIdx.x - kConvWarp0 * 32;
             PipeState pst, cst;
+            long long t_cfull = 0, t_cempty = 0, t_conv = 0;
             // offset removed from the magic-biased value: 128/1024 (+8 when the nibble is offset-binary)
             typename Tr::T2 offA2, offB2;
             {
@@ -658,19 +726,29 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const uint32_t offB = *reinterpret_cast<uint32_t *>(&offB2);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < num_kblocks; kb++) {
-                    mbar_wait(&s.full[pst.idx], pst.phase);
-                    mbar_wait(&s.cempty[cst.idx], cst.phase ^ 1);
+                    NB200_TIMED(t_cfull, mbar_wait(&s.full[pst.idx], pst.phase));
+                    NB200_TIMED(t_cempty, mbar_wait(&s.cempty[cst.idx], cst.phase ^ 1));
+                    const long long t_c0 = clock64();
                     convert_unit<hT>(s.a[pst.idx], s.a_cv[cst.idx], ct, reinterpret_cast<const hT *>(s.sa[pst.idx]), offA);
 #pragma unroll
                     for (int i = 0; i < BN / 128; i++)
                         convert_unit<hT>(s.b[pst.idx], s.b_cv[cst.idx], ct + i * kNumConvThreads,
                                          reinterpret_cast<const hT *>(s.sb[pst.idx]), offB);
                     fence_proxy_async_smem();
-                    mbar_arrive(&s.cfull[cst.idx]);
-                    mbar_arrive(&s.empty[pst.idx]);
+                    __syncwarp();
+                    if (lane == 0) {  // one arrival per warp: 512 per-thread arrivals per k-block serialise on one word
+                        mbar_arrive(&s.cfull[cst.idx]);
+                        mbar_arrive(&s.empty[pst.idx]);
+                    }
+                    t_conv += clock64() - t_c0;
                     pst.advance(C::kStages);
                     cst.advance(C::kConvStages);
                 }
+            }
+            if (p.prof && ct == 0) {
+                p.prof[blockIdx.x * 16 + 6] = t_cfull;
+                p.prof[blockIdx.x * 16 + 7] = t_cempty;
+                p.prof[blockIdx.x * 16 + 8] = t_conv;
             }
         }
     }
@@ -678,6 +756,10 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     // ---- teardown -------------------------------------------------------------------------------
     tc_fence_before_sync();
     __syncthreads();
+    if (p.prof && threadIdx.x == 0) {
+        p.prof[blockIdx.x * 16 + 9] = clock64() - t_kernel0;
+        p.prof[blockIdx.x * 16 + 12] = t_setup;
+    }
     if (warp == 2) {
         tc_fence_after_sync();
         tmem_dealloc<512>(tmem_base);
@@ -737,6 +819,7 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.num_tiles = (a.Mp / BM) * p.num_n_blocks;
     p.mid_act = a.mid_act;
     p.act_unsigned = a.act_unsigned;
+    p.prof = static_cast<long long *>(a.prof);
     p.out = a.out;
     p.qout = static_cast<uint8_t *>(a.qout);
     p.oscales_out = a.oscales;

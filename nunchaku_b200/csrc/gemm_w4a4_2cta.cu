@@ -45,6 +45,7 @@ struct Gemm2Params {
     int Mp, N, K, R, Rp;
     int num_n_blocks, num_tiles;   // pair tiles
     int mid_act, act_unsigned;
+    long long *prof;  // optional [grid][16] cycle counters (tools/gemm_prof.py)
     float lora_scales[NB200_MAX_LORA_SCALES];
 };
 
@@ -59,7 +60,9 @@ struct Cfg2 {
     static constexpr int kSbBytes = FP4 ? 2 * 4 * 512 : BH * 2;    // FP4: SFB of ALL 256 columns
     static constexpr int kTmemSfa = kNumAcc * BN;
     static constexpr int kTmemSfb = kTmemSfa + 16;
-    static constexpr int kThreads = FP4 ? 256 : 512;
+    static constexpr int kEpiGroups = FP4 ? 2 : 1;   // see gemm_w4a4.cu: FP4 tiles are epilogue bound
+    static constexpr int kEpiThreads = 128 * kEpiGroups;
+    static constexpr int kThreads = FP4 ? (4 + 4 * kEpiGroups) * 32 : 512;
     static_assert(!FP4 || kTmemSfb + 32 <= 512, "TMEM budget");
 };
 
@@ -88,6 +91,14 @@ struct alignas(1024) Smem2 {
     uint64_t lora_empty;             // multicast commit
     uint32_t tmem_base;
 };
+
+// cycle accounting of the barrier waits (written out only when p.prof != nullptr)
+#define NB200_TIMED(acc, stmt)            \
+    do {                                  \
+        const long long _t0 = clock64();  \
+        stmt;                             \
+        (acc) += clock64() - _t0;         \
+    } while (0)
 
 struct PipeState {
     uint32_t idx = 0, phase = 0;
@@ -166,6 +177,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
     extern __shared__ uint8_t smem_raw[];
     S &s = *reinterpret_cast<S *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
 
+    const long long t_kernel0 = clock64();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -189,18 +201,18 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < C::kStages; i++) {
             mbar_init(&s.full[i], 1);
-            mbar_init(&s.empty[i], FP4 ? 1 : kNumConvThreads);
+            mbar_init(&s.empty[i], FP4 ? 1 : kNumConvThreads / 32);
         }
         for (int i = 0; i < C::kConvStages; i++) {
-            mbar_init(&s.cfull[i], 2 * kNumConvThreads);
+            mbar_init(&s.cfull[i], 2 * kNumConvThreads / 32);
             mbar_init(&s.cempty[i], 1);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&s.tmem_full[i], 1);
-            mbar_init(&s.tmem_empty[i], 2 * kNumEpiThreads);
+            mbar_init(&s.tmem_empty[i], 2 * C::kEpiThreads);
         }
         mbar_init(&s.lora_b_full, 1);
-        mbar_init(&s.lora_a_full, 2 * kNumEpiThreads);
+        mbar_init(&s.lora_a_full, 2 * C::kEpiThreads);
         mbar_init(&s.lora_empty, 1);
         fence_mbar_init();
     }
@@ -209,19 +221,21 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
     cluster_sync();
     tc_fence_after_sync();
     const uint32_t tmem_base = s.tmem_base;
+    const long long t_setup = clock64() - t_kernel0;
 
     if (warp == 0) {
         // =================================== TMA producer (both CTAs) ===============================
         if (elect_one()) {
             PipeState st;
             uint32_t lora_phase = 0;
+            long long t_empty = 0;
             for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
                 const int mb2 = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
                 const int m0 = mb2 * 2 * BM + rank * BM;   // this CTA's A rows
                 const int n0 = nb * BN;
                 const int nh = n0 + rank * BH;             // this CTA's B rows
                 for (int kb = 0; kb < num_kblocks; kb++) {
-                    mbar_wait(&s.empty[st.idx], st.phase ^ 1);
+                    NB200_TIMED(t_empty, mbar_wait(&s.empty[st.idx], st.phase ^ 1));
                     if constexpr (FP4) {
                         // the leader's barrier collects the bytes of both CTAs
                         // (scale-factor boxes are always 4 tiles = 2 KB, also on the K tail)
@@ -251,6 +265,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                     lora_phase ^= 1;
                 }
             }
+            if (p.prof) p.prof[blockIdx.x * 16 + 0] = t_empty;
         }
     } else if (warp == 1) {
         // ==================================== MMA issuer (leader CTA) ================================
@@ -259,16 +274,19 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
             uint32_t lora_phase = 0;
             uint32_t acc_phase[2] = {0, 0};
             int it = 0;
+            long long t_tmem_empty = 0, t_full = 0, t_lora = 0, t_first = 0;
+            const long long t_mma0 = clock64();
             constexpr uint32_t idesc_main = FP4 ? make_idesc_nvf4(2 * BM, BN) : make_idesc_f16(Tr::kIsBf16, 2 * BM, BN);
             constexpr uint32_t idesc_lora = make_idesc_f16(Tr::kIsBf16, 2 * BM, BN);
             for (int tile = pair; tile < p.num_tiles; tile += num_pairs, it++) {
                 const int acc = it % C::kNumAcc;
-                mbar_wait_cluster(&s.tmem_empty[acc], acc_phase[acc] ^ 1);
+                NB200_TIMED(t_tmem_empty, mbar_wait_cluster(&s.tmem_empty[acc], acc_phase[acc] ^ 1));
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     if constexpr (FP4) {
-                        mbar_wait_cluster(&s.full[st.idx], st.phase);
+                        NB200_TIMED(t_full, mbar_wait_cluster(&s.full[st.idx], st.phase));
+                        if (t_first == 0) t_first = clock64() - t_mma0;
                         tc_fence_after_sync();
                         const int nj = min(4, k64_total - 4 * kb);
                         for (int j = 0; j < nj; j++) {
@@ -288,7 +306,8 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                         tc_commit_cg2(&s.empty[st.idx], 3);
                         st.advance(C::kStages);
                     } else {
-                        mbar_wait_cluster(&s.cfull[st.idx], st.phase);
+                        NB200_TIMED(t_full, mbar_wait_cluster(&s.cfull[st.idx], st.phase));
+                        if (t_first == 0) t_first = clock64() - t_mma0;
                         tc_fence_after_sync();
                         const uint32_t a_addr = smem_u32(s.a_cv[st.idx]), b_addr = smem_u32(s.b_cv[st.idx]);
 #pragma unroll
@@ -300,8 +319,8 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                     }
                 }
                 for (int c = 0; c < lora_chunks; c++) {
-                    mbar_wait_cluster(&s.lora_b_full, lora_phase);
-                    mbar_wait_cluster(&s.lora_a_full, lora_phase);
+                    NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_b_full, lora_phase));
+                    NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_a_full, lora_phase));
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem_u32(s.lora_a), b_addr = smem_u32(s.lora_b);
 #pragma unroll
@@ -314,35 +333,50 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                 tc_commit_cg2(&s.tmem_full[acc], 3);
                 acc_phase[acc] ^= 1;
             }
+            if (p.prof) {
+                p.prof[blockIdx.x * 16 + 1] = t_tmem_empty;
+                p.prof[blockIdx.x * 16 + 2] = t_full;
+                p.prof[blockIdx.x * 16 + 3] = t_lora;
+                p.prof[blockIdx.x * 16 + 10] = clock64() - t_mma0;
+                p.prof[blockIdx.x * 16 + 13] = t_first;
+            }
         }
-    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4 * C::kEpiGroups) {
         // ===================================== epilogue (both CTAs) ==================================
-        const int q = warp - kEpiWarp0;
-        const int et = threadIdx.x - kEpiWarp0 * 32;
+        constexpr int H = C::kEpiGroups;
+        constexpr int CH = BN / 64;
+        const int h = (warp - kEpiWarp0) >> 2;
+        const int q = warp & 3;
+        const int et = threadIdx.x - (kEpiWarp0 + 4 * h) * 32;
+        const int eta = threadIdx.x - kEpiWarp0 * 32;
         const int row = q * 32 + lane;
         uint32_t lora_phase = 0;
         uint32_t acc_phase[2] = {0, 0};
         int it = 0;
         uint32_t store_count = 0;
+        long long t_tmem_full = 0, t_pre = 0;
+        const long long t_epi0 = clock64();
         const uint32_t lora_a_full_leader = mapa(smem_u32(&s.lora_a_full), 0);
         for (int tile = pair; tile < p.num_tiles; tile += num_pairs, it++) {
             const int mb2 = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
             const int m0 = mb2 * 2 * BM + rank * BM, n0 = nb * BN;
             const int acc = it % C::kNumAcc;
+            const long long t_tile0 = clock64();
 
-            named_bar_sync(1, kNumEpiThreads);
-            for (int i = et; i < BN; i += kNumEpiThreads) {
+            named_bar_sync(1, C::kEpiThreads);
+            for (int i = eta; i < BN; i += C::kEpiThreads) {
                 s.bias[i] = p.bias != nullptr ? p.bias[n0 + i] : 0.f;
                 s.cscale[i] = p.cscale != nullptr ? p.cscale[n0 + i] : 1.f;
             }
-            named_bar_sync(1, kNumEpiThreads);
+            named_bar_sync(1, C::kEpiThreads);
 
             for (int c = 0; c < lora_chunks; c++) {
                 mbar_wait(&s.lora_empty, lora_phase ^ 1);
                 const float *src = p.lora_act + static_cast<size_t>(m0 + row) * p.R + c * kLoraChunk;
                 uint8_t *dst = s.lora_a + (row >> 3) * 512 + (row & 7) * 16;
 #pragma unroll
-                for (int o = 0; o < 4; o++) {
+                for (int oo = 0; oo < 4 / H; oo++) {
+                    const int o = h * (4 / H) + oo;
                     const int r0 = c * kLoraChunk + o * 8;
                     uint32_t w[4] = {0, 0, 0, 0};
                     if (r0 < p.R) {
@@ -365,24 +399,31 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                 lora_phase ^= 1;
             }
 
-            mbar_wait(&s.tmem_full[acc], acc_phase[acc]);
+            t_pre += clock64() - t_tile0;
+            NB200_TIMED(t_tmem_full, mbar_wait(&s.tmem_full[acc], acc_phase[acc]));
             acc_phase[acc] ^= 1;
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
             const uint32_t tmem_empty_leader = mapa(smem_u32(&s.tmem_empty[acc]), 0);
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 64; ch++) {
+            for (int cc = 0; cc < CH / H; cc++) {
+                const int ch = h * (CH / H) + cc;
                 uint32_t v0[32], v1[32];
                 tmem_ld_32x32b_x32(taddr + ch * 64, v0);
                 tmem_ld_32x32b_x32(taddr + ch * 64 + 32, v1);
                 tmem_ld_wait();
-                if (ch == BN / 64 - 1) {
+                if (cc == CH / H - 1) {
                     tc_fence_before_sync();
                     mbar_arrive_cluster(tmem_empty_leader);
                 }
-                const int buf = store_count & 1;
-                if (et == 0) bulk_wait_group_read<1>();
-                named_bar_sync(2, kNumEpiThreads);
+                const int buf = H == 2 ? h : (store_count & 1);
+                if (et == 0) {
+                    if constexpr (H == 2)
+                        bulk_wait_group_read<0>();
+                    else
+                        bulk_wait_group_read<1>();
+                }
+                named_bar_sync(2 + 2 * h, kNumEpiThreads);
                 uint8_t *srow = s.out_stage[buf] + row * 128;
 #pragma unroll
                 for (int c8 = 0; c8 < 8; c8++) {
@@ -414,7 +455,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                     *reinterpret_cast<uint4 *>(srow + ((c8 ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(3, kNumEpiThreads);
+                named_bar_sync(3 + 2 * h, kNumEpiThreads);
                 if (et == 0) {
                     tma_store_2d(&tm_out, s.out_stage[buf], n0 + ch * 64, m0);
                     bulk_commit_group();
@@ -423,11 +464,17 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
             }
         }
         if (et == 0) bulk_wait_group<0>();
+        if (p.prof && eta == 0) {
+            p.prof[blockIdx.x * 16 + 4] = t_tmem_full;
+            p.prof[blockIdx.x * 16 + 5] = clock64() - t_epi0;
+            p.prof[blockIdx.x * 16 + 11] = t_pre;
+        }
     } else if (!FP4 && warp >= kConvWarp0) {
         // ============================ INT4 -> hT converter warps (both CTAs) ===========================
         if constexpr (!FP4) {
             const int ct = threadIdx.x - kConvWarp0 * 32;
             PipeState pst, cst;
+            long long t_cfull = 0, t_cempty = 0, t_conv = 0;
             typename Tr::T2 offA2, offB2;
             {
                 const float base = Tr::kIsBf16 ? 128.f : 1024.f;
@@ -442,16 +489,26 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
             const uint32_t offB = *reinterpret_cast<uint32_t *>(&offB2);
             for (int tile = pair; tile < p.num_tiles; tile += num_pairs) {
                 for (int kb = 0; kb < num_kblocks; kb++) {
-                    mbar_wait(&s.full[pst.idx], pst.phase);
-                    mbar_wait(&s.cempty[cst.idx], cst.phase ^ 1);
+                    NB200_TIMED(t_cfull, mbar_wait(&s.full[pst.idx], pst.phase));
+                    NB200_TIMED(t_cempty, mbar_wait(&s.cempty[cst.idx], cst.phase ^ 1));
+                    const long long t_c0 = clock64();
                     convert_unit<hT>(s.a[pst.idx], s.a_cv[cst.idx], ct, reinterpret_cast<const hT *>(s.sa[pst.idx]), offA);
                     convert_unit<hT>(s.b[pst.idx], s.b_cv[cst.idx], ct, reinterpret_cast<const hT *>(s.sb[pst.idx]), offB);
                     fence_proxy_async_smem();
-                    mbar_arrive_cluster(mapa(smem_u32(&s.cfull[cst.idx]), 0));
-                    mbar_arrive(&s.empty[pst.idx]);
+                    __syncwarp();
+                    if (lane == 0) {  // one arrival per warp: 512 per-thread (remote) arrivals per k-block serialise on one word
+                        mbar_arrive_cluster(mapa(smem_u32(&s.cfull[cst.idx]), 0));
+                        mbar_arrive(&s.empty[pst.idx]);
+                    }
+                    t_conv += clock64() - t_c0;
                     pst.advance(C::kStages);
                     cst.advance(C::kConvStages);
                 }
+            }
+            if (p.prof && ct == 0) {
+                p.prof[blockIdx.x * 16 + 6] = t_cfull;
+                p.prof[blockIdx.x * 16 + 7] = t_cempty;
+                p.prof[blockIdx.x * 16 + 8] = t_conv;
             }
         }
     }
@@ -459,6 +516,10 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
     // both CTAs must stay alive until the pair's MMAs and remote arrivals are done
     tc_fence_before_sync();
     cluster_sync();
+    if (p.prof && threadIdx.x == 0) {
+        p.prof[blockIdx.x * 16 + 9] = clock64() - t_kernel0;
+        p.prof[blockIdx.x * 16 + 12] = t_setup;
+    }
     if (warp == 2) {
         tc_fence_after_sync();
         tmem_dealloc_cg2<512>(tmem_base);
@@ -510,6 +571,7 @@ int launch2(const nb200_gemm_args &a, cudaStream_t stream) {
     p.num_tiles = (a.Mp / (2 * BM)) * p.num_n_blocks;
     p.mid_act = a.mid_act;
     p.act_unsigned = a.act_unsigned;
+    p.prof = static_cast<long long *>(a.prof);
     for (int i = 0; i < NB200_MAX_LORA_SCALES; i++) p.lora_scales[i] = a.lora_scales[i];
 
     static int num_sms_cached = 0;

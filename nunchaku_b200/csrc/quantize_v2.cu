@@ -24,8 +24,8 @@ namespace {
 using namespace ptx;
 
 constexpr int kRows = 32;
-constexpr int kConsumers = 8;
-constexpr int kStages = 16;
+constexpr int kConsumers = 16;   // 4 warps per scheduler: the kernel is issue/latency bound, not bandwidth bound
+constexpr int kStages = 32;      // two tiles in flight per consumer warp (128 KB of TMA traffic outstanding)
 constexpr int kThreads = (kConsumers + 1) * 32;
 constexpr int kTileBytes = kRows * 128;
 
@@ -132,55 +132,83 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                 const uint32_t it = it_base + i;
                 const uint32_t st = it % kStages, ph = (it / kStages) & 1;
                 // B fragments (L2 resident) and smoothing factors first: independent of the tile
-                uint4 bw[2][4];
+                uint4 bw[4];   // B fragments of the first 32-wide half; the second half is fetched after it is consumed
 #pragma unroll
-                for (int kb = 0; kb < 2; kb++)
+                for (int j = 0; j < 4; j++)
+                    bw[j] = ldg_v4(ldw + (static_cast<size_t>(g * 2) * nt_total + chunk * 4 + j) * 32 + lane);
+                // x / smooth as the reference's __fdividef computes it (gemm_utils.cuh:329-344): SASS is
+                // "if |b| < 2^-126 scale a and b by 2^24; MUFU.RCP(b) * a".  The reciprocal and the scale depend
+                // only on the column, so they are hoisted out of the 8 row passes of the tile.
+                float rsm[8], ksm[8];
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        bw[kb][j] = ldg_v4(ldw + (static_cast<size_t>(g * 2 + kb) * nt_total + chunk * 4 + j) * 32 + lane);
-                uint4 sm = make_uint4(0, 0, 0, 0);
-                if (chunk == 0 && smooth != nullptr) sm = ldg_v4(smooth + g * 64 + c * 8);
+                for (int e = 0; e < 8; e++) {
+                    rsm[e] = 1.f;
+                    ksm[e] = 1.f;
+                }
+                if (chunk == 0 && smooth != nullptr) {
+                    const uint4 sm = ldg_v4(smooth + g * 64 + c * 8);
+                    const uint32_t sw[4] = {sm.x, sm.y, sm.z, sm.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float2 b = Tr::to_float2(*reinterpret_cast<const T2 *>(&sw[e]));
+                        const float bb[2] = {b.x, b.y};
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            const bool tiny = fabsf(bb[u]) < 1.175494350822287508e-38f;
+                            ksm[2 * e + u] = tiny ? 16777216.f : 1.f;
+                            rsm[2 * e + u] = rcp_approx(tiny ? bb[u] * 16777216.f : bb[u]);
+                        }
+                    }
+                }
 
                 mbar_wait(&s.full[st], ph);
                 const uint32_t tile = smem_u32(s.tile[st]);
 
                 // ---- x @ lora_down^T on the un-smoothed tile (lora.cuh:243-353) ---------------------
 #pragma unroll
-                for (int m = 0; m < 2; m++) {
+                for (int kb = 0; kb < 2; kb++) {
 #pragma unroll
-                    for (int kstep = 0; kstep < 4; kstep++) {
-                        const int r = m * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-                        const int ch = kstep * 2 + (lane >> 4);
-                        uint32_t a[4];
-                        ldmatrix_x4(tile + r * 128 + ((ch ^ (r & 7)) << 4), a);
+                    for (int m = 0; m < 2; m++) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint4 &b = bw[kstep >> 1][j];
-                            if (kstep & 1)
-                                mma16816<hT>(acc[m][j], a, b.z, b.w);
-                            else
-                                mma16816<hT>(acc[m][j], a, b.x, b.y);
+                        for (int k2 = 0; k2 < 2; k2++) {
+                            const int kstep = kb * 2 + k2;
+                            const int r = m * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+                            const int ch = kstep * 2 + (lane >> 4);
+                            uint32_t a[4];
+                            ldmatrix_x4(tile + r * 128 + ((ch ^ (r & 7)) << 4), a);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                if (k2)
+                                    mma16816<hT>(acc[m][j], a, bw[j].z, bw[j].w);
+                                else
+                                    mma16816<hT>(acc[m][j], a, bw[j].x, bw[j].y);
+                            }
                         }
+                    }
+                    if (kb == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            bw[j] = ldg_v4(ldw + (static_cast<size_t>(g * 2 + 1) * nt_total + chunk * 4 + j) * 32 + lane);
                     }
                 }
 
                 // ---- smooth + quantise: 8 lanes per row, 4 rows per pass (gemm_w4a4.cuh:85-187,429-523) --
                 if (chunk == 0) {
-#pragma unroll 2
+#pragma unroll 1
                     for (int pass = 0; pass < kRows / 4; pass++) {
                         const int r = pass * 4 + r4;
                         const int m = row0 + r;
                         const uint4 xv = *reinterpret_cast<const uint4 *>(s.tile[st] + r * 128 + ((c ^ (r & 7)) << 4));
                         const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                        const uint32_t sw[4] = {sm.x, sm.y, sm.z, sm.w};
                         float xs[8];
                         float amax = 0.f;
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             float2 a = Tr::to_float2(*reinterpret_cast<const T2 *>(&xw[e]));
                             if (smooth != nullptr) {
-                                const float2 b = Tr::to_float2(*reinterpret_cast<const T2 *>(&sw[e]));
-                                a = Tr::to_float2(Tr::from_float2(make_float2(__fdividef(a.x, b.x), __fdividef(a.y, b.y))));
+                                a.x = (a.x * ksm[2 * e]) * rsm[2 * e];
+                                a.y = (a.y * ksm[2 * e + 1]) * rsm[2 * e + 1];
+                                a = Tr::to_float2(Tr::from_float2(a));   // h2div rounds the quotient to hT
                             }
                             xs[2 * e] = a.x;
                             xs[2 * e + 1] = a.y;
@@ -307,7 +335,7 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
     int ks = 1;
     if (a.workspace != nullptr && row_blocks < 96 && p.Rp == 32) {
         ks = (160 + row_blocks - 1) / row_blocks;
-        if (ks > G / kConsumers) ks = G / kConsumers;
+        if (ks > G / 4) ks = G / 4;   // at least 4 groups (256 k) per CTA
         if (ks < 1) ks = 1;
         const size_t need = static_cast<size_t>(ks) * a.Mp * 32 * sizeof(float) + static_cast<size_t>(row_blocks) * sizeof(unsigned int);
         if (need > static_cast<size_t>(a.workspace_bytes)) ks = 1;

@@ -13,6 +13,7 @@ from ..utils import torch_dtype_code
 # tuning knobs for experiments (0 = let the launcher choose)
 BLOCK_N_OVERRIDE = 0
 NUM_SMS_OVERRIDE = 0
+PROF_BUFFER = None   # torch int64 tensor [grid, 16]: per-CTA barrier-wait cycle counters (tools/gemm_prof.py)
 
 
 def svdq_gemm_w4a4_cuda(
@@ -141,6 +142,7 @@ def svdq_gemm_w4a4_cuda(
     args.mid_act = NB200_ACT_SILU if fuse_silu else NB200_ACT_NONE
     args.block_n = BLOCK_N_OVERRIDE
     args.num_sms = NUM_SMS_OVERRIDE
+    args.prof = None if PROF_BUFFER is None else PROF_BUFFER.data_ptr()
     check(lib.nb200_gemm_w4a4(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "gemm_w4a4")
 
 

@@ -48,4 +48,4 @@ def test_struct_layout_matches_header_sizes():
     from nunchaku_b200._C import GemmArgs, QuantizeArgs
 
     assert ctypes.sizeof(QuantizeArgs) == 96
-    assert ctypes.sizeof(GemmArgs) == 17 * 8 + 11 * 4 + 64 * 4 + 2 * 4 + 4  # + tail padding to 8
+    assert ctypes.sizeof(GemmArgs) == 456

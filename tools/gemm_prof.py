@@ -1,0 +1,66 @@
+"""Barrier-wait cycle breakdown of the fused GEMM (device-side clock64 counters, p.prof).
+
+    python tools/gemm_prof.py [--precision int4|nvfp4|both] [--M 4096 --K 3072 --N 3072] [--bn 0,512]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import torch  # noqa: E402
+
+from op_sweep import make_layer  # noqa: E402
+
+SLOTS = {9: "KERNEL total", 12: "setup (alloc, barriers, sync)", 13: "mma: first operands ready", 0: "producer wait empty", 1: "mma wait tmem_empty", 2: "mma wait operands(full/cfull)", 3: "mma wait lora",
+         10: "mma loop total", 4: "epi wait tmem_full", 11: "epi pre-tile work (bias+lora cvt)", 5: "epi loop total",
+         6: "conv wait TMA(full)", 7: "conv wait cempty", 8: "conv busy"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="both")
+    ap.add_argument("--M", type=int, default=4096)
+    ap.add_argument("--K", type=int, default=3072)
+    ap.add_argument("--N", type=int, default=3072)
+    ap.add_argument("--bn", default="0,512")
+    args = ap.parse_args()
+    from nunchaku_b200.ops import gemm as G
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(0)
+    for prec in (["int4", "nvfp4"] if args.precision == "both" else [args.precision]):
+        m = make_layer(args.K, args.N, 32, prec, torch.bfloat16, dev, g)
+        x = torch.randn(args.M, args.K, generator=g, device=dev).to(torch.bfloat16)
+        q, s, la = m.quantize(x)
+        out = torch.empty(args.M, args.N, dtype=torch.bfloat16, device=dev)
+        for bn in [int(b) for b in args.bn.split(",")]:
+            G.BLOCK_N_OVERRIDE = bn
+            for _ in range(3):
+                m.forward_quant(q, s, la, out)
+            prof = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+            G.PROF_BUFFER = prof
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(2e7))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            m.forward_quant(q, s, la, out)
+            e1.record()
+            torch.cuda.synchronize()
+            G.PROF_BUFFER = None
+            G.BLOCK_N_OVERRIDE = 0
+            us = e0.elapsed_time(e1) * 1e3
+            pr = prof.cpu().double()
+            used = pr[:, 10] > 0 if bn != 512 else pr[:, 5] > 0
+            print(f"== {prec} M={args.M} K={args.K} N={args.N} bn={bn}: {us:.1f} us  ({2*args.M*args.K*args.N/us/1e6:.0f} TFLOP/s)  CTAs with data {int(used.sum())}")
+            for k, name in SLOTS.items():
+                col = pr[:, k]
+                nz = col[col > 0]
+                if nz.numel():
+                    print(f"   {name:36s} mean {nz.mean().item()/1e3:9.1f} kclk   max {nz.max().item()/1e3:9.1f} kclk   ({nz.numel()} CTAs)")
+
+
+if __name__ == "__main__":
+    main()

@@ -35,19 +35,23 @@ def make_layer(K, N, R, precision, dtype, dev, g):
 
 
 def time_fn(fn, iters, flush):
+    """CUDA-event time of fn() with L2 flushed before every call.  A long spin kernel is queued first
+    so that the CPU enqueues the whole [flush, event, fn, event] train while the GPU is still busy:
+    no launch-latency gap hides inside an event pair."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    ts = []
+    torch.cuda._sleep(int(6e7))   # ~30 ms at 1.9 GHz
+    evs = []
     for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    ts.sort()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
     return ts[len(ts) // 2], ts[0]
 
 
