@@ -36,7 +36,12 @@ constexpr int BM = 128;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiThreads = 128;
 constexpr int kConvWarp0 = 8;
-constexpr int kNumConvThreads = 256;
+// INT4: 24 converter warps -> one 32-element unit per thread per k block (128x64 A + 256x64 B = 768 units).
+// Measured with 8 warps (3 units per thread): the converters were busy 75 % of the kernel and the MMA warp
+// starved 85 % of it; the work is latency bound (LDS -> LOP3 -> HSUB2 -> HMUL2 -> STS chains), so it is
+// spread over more warps and the register file is re-balanced with setmaxnreg (1024 threads x 64 regs).
+constexpr int kConvWarps = 24;
+constexpr int kNumConvThreads = kConvWarps * 32;
 constexpr int kLoraChunk = 32;  // ranks per low-rank MMA group (2 x K16)
 
 struct GemmParams {
@@ -90,7 +95,7 @@ struct Cfg {
     // warps already fill the register file).
     static constexpr int kEpiGroups = FP4 ? 2 : 1;
     static constexpr int kEpiThreads = 128 * kEpiGroups;
-    static constexpr int kThreads = FP4 ? (4 + 4 * kEpiGroups) * 32 : 512;
+    static constexpr int kThreads = FP4 ? (4 + 4 * kEpiGroups) * 32 : (kConvWarp0 + kConvWarps) * 32;
     static_assert(!FP4 || kTmemSfb + kSfbCols <= 512, "TMEM budget");
     static_assert(kNumAcc * BN <= 512, "TMEM budget");
     static_assert(EPI != EPI_QUANT || (BN == 128 && kTmemLd + kMaxRdp <= 512), "fused quantise epilogue uses 128-wide tiles");
@@ -245,7 +250,11 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     const uint32_t tmem_base = s.tmem_base;
     const long long t_setup = clock64() - t_kernel0;
 
-    if (warp == 0) {
+    // INT4: 1024 threads start with 64 registers each; every warp group (4 warps) re-sizes its share as the first
+    // instruction of its role: producer/MMA/alloc group 56, epilogue group 128, the six converter groups 48.
+    if (warp < 4) {
+      if constexpr (!FP4) setmaxnreg_dec<56>();
+      if (warp == 0) {
         // =================================== TMA producer =======================================
         if (elect_one()) {
             PipeState st;
@@ -302,7 +311,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             }
             if (p.prof) p.prof[blockIdx.x * 16 + 0] = t_empty;
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ==================================== MMA issuer ========================================
         if (elect_one()) {
             PipeState st;   // FP4: TMA ring.  INT4: converted ring
@@ -376,7 +385,9 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 p.prof[blockIdx.x * 16 + 13] = t_first;
             }
         }
+      }
     } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4 * C::kEpiGroups) {
+        if constexpr (!FP4) setmaxnreg_inc<128>();
         // ===================================== epilogue ==========================================
         constexpr int H = C::kEpiGroups;       // half-groups of 4 warps; group h owns column chunks [h*CH/H, (h+1)*CH/H)
         constexpr int CH = BN / 64;
@@ -493,17 +504,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 }
             }
 
-#pragma unroll 1
-            for (int cc = 0; cc < CH / H; cc++) {
-                const int ch = h * (CH / H) + cc;
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32b_x32(taddr + ch * 64, v0);
-                tmem_ld_32x32b_x32(taddr + ch * 64 + 32, v1);
-                tmem_ld_wait();
-                if (cc == CH / H - 1) {
-                    tc_fence_before_sync();
-                    mbar_arrive(&s.tmem_empty[acc]);
-                }
+            // one 64-column chunk: scale/bias/activation, hT pack into the swizzled staging tile, TMA store
+            auto do_chunk = [&](const int ch, const uint32_t (&v0)[32], const uint32_t (&v1)[32]) {
                 // staging buffer: one group -> two buffers alternate; two groups -> one buffer each
                 const int buf = H == 2 ? h : (store_count & 1);
                 if (et == 0) {
@@ -675,6 +677,37 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     }
                 }
                 store_count++;
+            };
+            // FP4 with a single 256-column accumulator: pull this group's two chunks into registers first and
+            // hand the accumulator back to the MMA warp before doing any math (the exposed part of the epilogue
+            // shrinks from "drain + math + stores" to four tcgen05.ld).
+            constexpr bool kEarlyRelease = FP4 && C::kNumAcc == 1 && CH / H == 2 && EPI == EPI_DEFAULT;
+            if constexpr (kEarlyRelease) {
+                uint32_t va[32], vb[32], vc[32], vd[32];
+                const int ch0 = h * 2;
+                tmem_ld_32x32b_x32(taddr + ch0 * 64, va);
+                tmem_ld_32x32b_x32(taddr + ch0 * 64 + 32, vb);
+                tmem_ld_32x32b_x32(taddr + ch0 * 64 + 64, vc);
+                tmem_ld_32x32b_x32(taddr + ch0 * 64 + 96, vd);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                mbar_arrive(&s.tmem_empty[acc]);
+                do_chunk(ch0, va, vb);
+                do_chunk(ch0 + 1, vc, vd);
+            } else {
+#pragma unroll 1
+                for (int cc = 0; cc < CH / H; cc++) {
+                    const int ch = h * (CH / H) + cc;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(taddr + ch * 64, v0);
+                    tmem_ld_32x32b_x32(taddr + ch * 64 + 32, v1);
+                    tmem_ld_wait();
+                    if (cc == CH / H - 1) {
+                        tc_fence_before_sync();
+                        mbar_arrive(&s.tmem_empty[acc]);
+                    }
+                    do_chunk(ch, v0, v1);
+                }
             }
             if constexpr (EPI == EPI_QUANT) {
                 if (p.R_down > 0) {
@@ -708,6 +741,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     } else if (!FP4 && warp >= kConvWarp0) {
         // ============================ INT4 -> hT converter warps ===================================
         if constexpr (!FP4) {
+            setmaxnreg_dec<48>();
             const int ct = threadIdx.x - kConvWarp0 * 32;
             PipeState pst, cst;
             long long t_cfull = 0, t_cempty = 0, t_conv = 0;
@@ -729,11 +763,10 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     NB200_TIMED(t_cfull, mbar_wait(&s.full[pst.idx], pst.phase));
                     NB200_TIMED(t_cempty, mbar_wait(&s.cempty[cst.idx], cst.phase ^ 1));
                     const long long t_c0 = clock64();
-                    convert_unit<hT>(s.a[pst.idx], s.a_cv[cst.idx], ct, reinterpret_cast<const hT *>(s.sa[pst.idx]), offA);
-#pragma unroll
-                    for (int i = 0; i < BN / 128; i++)
-                        convert_unit<hT>(s.b[pst.idx], s.b_cv[cst.idx], ct + i * kNumConvThreads,
-                                         reinterpret_cast<const hT *>(s.sb[pst.idx]), offB);
+                    if (ct < 2 * BM)
+                        convert_unit<hT>(s.a[pst.idx], s.a_cv[cst.idx], ct, reinterpret_cast<const hT *>(s.sa[pst.idx]), offA);
+                    else if (ct - 2 * BM < 2 * BN)
+                        convert_unit<hT>(s.b[pst.idx], s.b_cv[cst.idx], ct - 2 * BM, reinterpret_cast<const hT *>(s.sb[pst.idx]), offB);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {  // one arrival per warp: 512 per-thread arrivals per k-block serialise on one word
@@ -862,6 +895,9 @@ int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
         return gemm_w4a4_2cta_dispatch(a, stream);
     }
     int bn = a.block_n;
+    // measured (tools/op_sweep.py, profiles/): the CTA-pair kernel wins once the main loop is long enough to
+    // amortise its fully exposed epilogue hand-off (M=4352, K=12288: 3.83 vs 3.61 PFLOP/s); shorter K loses
+    if (bn == 0 && FP4 && a.K >= 8192 && a.N % 256 == 0 && a.Mp >= 2048) return gemm_w4a4_2cta_dispatch(a, stream);
     if (bn == 0) bn = (a.N % 256 == 0 && (a.Mp / BM) * (a.N / 256) >= 96) ? 256 : 128;
     if (bn == 256 && a.N % 256 == 0) return launch<FP4, hT, 256, EPI_DEFAULT>(a, stream);
     if (bn == 128) return launch<FP4, hT, 128, EPI_DEFAULT>(a, stream);

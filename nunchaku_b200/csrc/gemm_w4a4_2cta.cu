@@ -405,17 +405,8 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
             const uint32_t tmem_empty_leader = mapa(smem_u32(&s.tmem_empty[acc]), 0);
-#pragma unroll 1
-            for (int cc = 0; cc < CH / H; cc++) {
-                const int ch = h * (CH / H) + cc;
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32b_x32(taddr + ch * 64, v0);
-                tmem_ld_32x32b_x32(taddr + ch * 64 + 32, v1);
-                tmem_ld_wait();
-                if (cc == CH / H - 1) {
-                    tc_fence_before_sync();
-                    mbar_arrive_cluster(tmem_empty_leader);
-                }
+            // one 64-column chunk: scale/bias/activation, hT pack into the swizzled staging tile, TMA store
+            auto do_chunk = [&](const int ch, const uint32_t (&v0)[32], const uint32_t (&v1)[32]) {
                 const int buf = H == 2 ? h : (store_count & 1);
                 if (et == 0) {
                     if constexpr (H == 2)
@@ -461,6 +452,37 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                     bulk_commit_group();
                 }
                 store_count++;
+            };
+            // FP4 with a single 256-column accumulator: pull this group's two chunks into registers first and
+            // hand the accumulator back to the MMA warp before doing any math (the exposed part of the epilogue
+            // shrinks from "drain + math + stores" to four tcgen05.ld).
+            constexpr bool kEarlyRelease = FP4 && C::kNumAcc == 1 && CH / H == 2;
+            if constexpr (kEarlyRelease) {
+                uint32_t va[32], vb[32], vc[32], vd[32];
+                const int ch0 = h * 2;
+                tmem_ld_32x32b_x32(taddr + ch0 * 64, va);
+                tmem_ld_32x32b_x32(taddr + ch0 * 64 + 32, vb);
+                tmem_ld_32x32b_x32(taddr + ch0 * 64 + 64, vc);
+                tmem_ld_32x32b_x32(taddr + ch0 * 64 + 96, vd);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                mbar_arrive_cluster(tmem_empty_leader);
+                do_chunk(ch0, va, vb);
+                do_chunk(ch0 + 1, vc, vd);
+            } else {
+#pragma unroll 1
+                for (int cc = 0; cc < CH / H; cc++) {
+                    const int ch = h * (CH / H) + cc;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(taddr + ch * 64, v0);
+                    tmem_ld_32x32b_x32(taddr + ch * 64 + 32, v1);
+                    tmem_ld_wait();
+                    if (cc == CH / H - 1) {
+                        tc_fence_before_sync();
+                        mbar_arrive_cluster(tmem_empty_leader);
+                    }
+                    do_chunk(ch, v0, v1);
+                }
             }
         }
         if (et == 0) bulk_wait_group<0>();
