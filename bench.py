@@ -301,16 +301,13 @@ def main() -> int:
         return run_reference_arm(args)
 
     import torch
-    import torch.distributed as dist
+    from nunchaku_b200 import replica
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = replica.world()
     assert torch.cuda.is_available(), "bench.py needs a GPU (use --impl reference for the CPU arm)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    replica.init("nccl", device)
     from nunchaku_b200._C import check, lib
 
     check(lib.nb200_check_device(), "check_device")
@@ -320,8 +317,8 @@ def main() -> int:
     n_layers = len(mods)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        torch.cuda.synchronize()
+        replica.barrier()
         torch.cuda.synchronize()
 
     # ---- warm-up (also triggers the one-time repack) -----------------------------------------
@@ -364,10 +361,7 @@ def main() -> int:
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = replica.max_over_ranks(ms, device)
     ms_per_step = ms_total / args.steps
     images_per_s = world * (1.0 / STEPS_PER_IMAGE) / (ms_per_step * 1e-3)
     f_main, f_lr = step_flops()
@@ -390,10 +384,7 @@ def main() -> int:
         torch.cuda.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_images = world * (1.0 / STEPS_PER_IMAGE) / (float(t.item()) / args.steps)
+    e2e_images = world * (1.0 / STEPS_PER_IMAGE) / (replica.max_over_ranks(e2e_s, device) / args.steps)
 
     # ---- roofline of the dominant kernel (fused GEMM), CUDA events on the launch stream ------------
     runner.step(record_gemm_events=True)
@@ -439,9 +430,7 @@ def main() -> int:
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    replica.shutdown()
     return 0
 
 

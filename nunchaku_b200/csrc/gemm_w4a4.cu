@@ -70,6 +70,8 @@ struct GemmParams {
     const void *norm_q, *norm_k;  // hT [128]
     const float *rotary;          // reference pack_rotemb layout [Mp][128]
     long long *prof;              // optional [grid][16] cycle counters (tools/gemm_prof.py)
+    int debug;                    // NB200_GEMM_DEBUG experiment bits (results invalid when non-zero): 1 = converters
+                                  // skip their smem stores, 2 = converters skip all work, 4 = no main-loop MMAs, 8 = epilogue drains TMEM but skips math/stores
     float lora_scales[NB200_MAX_LORA_SCALES];
 };
 
@@ -164,7 +166,7 @@ struct PipeState {
 // ---------------------------------------------------------------------------------------------
 template <typename hT>
 __device__ __forceinline__ void convert_unit(const uint8_t *pk_tile, uint8_t *cv_tile, int unit, const hT *scales,
-                                             uint32_t offset_bits) {
+                                             uint32_t offset_bits, int dbg_nostore = 0) {
     using Tr = HalfTraits<hT>;
     using T2 = typename Tr::T2;
     constexpr uint32_t kMagic = Tr::kIsBf16 ? 0x43004300u : 0x64006400u;  // 128 + u  |  1024 + u
@@ -188,6 +190,7 @@ __device__ __forceinline__ void convert_unit(const uint8_t *pk_tile, uint8_t *cv
             o[p] = *reinterpret_cast<uint32_t *>(&v);
         }
         const int chunk = (4 * h + w) ^ (r & 7);
+        if (dbg_nostore && (o[0] ^ o[1] ^ o[2] ^ o[3]) != 0x12345678u) continue;  // experiment: keep the math, drop the store
         *reinterpret_cast<uint4 *>(row + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
@@ -343,7 +346,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                                     make_smem_desc(smem_u32(s.sb[st.idx] + h * 2048 + j * 512), 0, 128, kLayoutNoSwizzle));
                         }
                         const uint32_t a_addr = smem_u32(s.a[st.idx]), b_addr = smem_u32(s.b[st.idx]);
-                        for (int j = 0; j < nj; j++)
+                        for (int j = 0; j < ((p.debug & 4) ? 0 : nj); j++)
                             tc_mma_nvf4(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
                                         idesc_main, tmem_base + C::kTmemSfa + 4 * j,
                                         tmem_base + C::kTmemSfb + (BN / 32) * j, (kb | j) != 0);
@@ -356,8 +359,9 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         const uint32_t a_addr = smem_u32(s.a_cv[st.idx]), b_addr = smem_u32(s.b_cv[st.idx]);
 #pragma unroll
                         for (int j = 0; j < 4; j++)
-                            tc_mma_f16(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
-                                       idesc_main, (kb | j) != 0);
+                            if (!(p.debug & 4))
+                                tc_mma_f16(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
+                                           idesc_main, (kb | j) != 0);
                         tc_commit(&s.cempty[st.idx]);
                         st.advance(C::kConvStages);
                     }
@@ -692,8 +696,10 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 tmem_ld_wait();
                 tc_fence_before_sync();
                 mbar_arrive(&s.tmem_empty[acc]);
-                do_chunk(ch0, va, vb);
-                do_chunk(ch0 + 1, vc, vd);
+                if (!(p.debug & 8)) {
+                    do_chunk(ch0, va, vb);
+                    do_chunk(ch0 + 1, vc, vd);
+                }
             } else {
 #pragma unroll 1
                 for (int cc = 0; cc < CH / H; cc++) {
@@ -706,7 +712,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         tc_fence_before_sync();
                         mbar_arrive(&s.tmem_empty[acc]);
                     }
-                    do_chunk(ch, v0, v1);
+                    if (!(p.debug & 8)) do_chunk(ch, v0, v1);
                 }
             }
             if constexpr (EPI == EPI_QUANT) {
@@ -763,10 +769,14 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     NB200_TIMED(t_cfull, mbar_wait(&s.full[pst.idx], pst.phase));
                     NB200_TIMED(t_cempty, mbar_wait(&s.cempty[cst.idx], cst.phase ^ 1));
                     const long long t_c0 = clock64();
-                    if (ct < 2 * BM)
-                        convert_unit<hT>(s.a[pst.idx], s.a_cv[cst.idx], ct, reinterpret_cast<const hT *>(s.sa[pst.idx]), offA);
-                    else if (ct - 2 * BM < 2 * BN)
-                        convert_unit<hT>(s.b[pst.idx], s.b_cv[cst.idx], ct - 2 * BM, reinterpret_cast<const hT *>(s.sb[pst.idx]), offB);
+                    if (!(p.debug & 2)) {
+                        if (ct < 2 * BM)
+                            convert_unit<hT>(s.a[pst.idx], s.a_cv[cst.idx], ct, reinterpret_cast<const hT *>(s.sa[pst.idx]), offA,
+                                             p.debug & 1);
+                        else if (ct - 2 * BM < 2 * BN)
+                            convert_unit<hT>(s.b[pst.idx], s.b_cv[cst.idx], ct - 2 * BM, reinterpret_cast<const hT *>(s.sb[pst.idx]),
+                                             offB, p.debug & 1);
+                    }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {  // one arrival per warp: 512 per-thread arrivals per k-block serialise on one word
@@ -853,6 +863,8 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.mid_act = a.mid_act;
     p.act_unsigned = a.act_unsigned;
     p.prof = static_cast<long long *>(a.prof);
+    static const int dbg = getenv("NB200_GEMM_DEBUG") ? atoi(getenv("NB200_GEMM_DEBUG")) : 0;
+    p.debug = dbg;
     p.out = a.out;
     p.qout = static_cast<uint8_t *>(a.qout);
     p.oscales_out = a.oscales;
