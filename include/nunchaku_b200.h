@@ -62,7 +62,7 @@ typedef enum nb200_status {
     NB200_ERR_ARCH = -4              /* device is not sm_100                            */
 } nb200_status;
 
-typedef enum nb200_dtype { NB200_FP16 = 0, NB200_BF16 = 1 } nb200_dtype;
+typedef enum nb200_dtype { NB200_FP16 = 0, NB200_BF16 = 1, NB200_FP32 = 2 /* glue ops only */ } nb200_dtype;
 
 /* mid-epilogue activation (reference: EpilogueNop / EpilogueSilu / EpilogueGelu) */
 typedef enum nb200_act { NB200_ACT_NONE = 0, NB200_ACT_SILU = 1, NB200_ACT_GELU = 2 } nb200_act;
@@ -162,6 +162,40 @@ typedef struct nb200_gemm_args {
 } nb200_gemm_args;
 
 int nb200_gemm_w4a4(const nb200_gemm_args *args, void *stream);
+
+/* ---- elementwise / row-reduce glue between the linears ------------------
+ * All tensors contiguous, 16-byte aligned, on the current device; dtype is an nb200_dtype.            */
+
+/* out = act(x);  kind = NB200_ACT_SILU (replaces Silu::forward, src/activation.cpp:4-8 -> vllm silu,
+ * kernels/activation_kernels_impl.cuh:7-10) or NB200_ACT_GELU (GELU::forward -> gelu_new, :93-97).        */
+int nb200_activation(int kind, int dtype, const void *x, void *out, long long numel, void *stream);
+
+/* out = LayerNorm(x) over the last dim, optional affine (weight / bias may be NULL); fp16 / bf16.
+ * Replaces LayerNorm::forward -> layernorm_general (src/layernorm.cpp:14-18, kernels/layernorm_kernels.cu:36-58). */
+int nb200_layernorm(int dtype, const void *x, const void *weight, const void *bias, void *out, long long rows, int hidden,
+                    float eps, void *stream);
+
+/* out = T(x * rsqrt(mean(x^2) + eps)) * weight.  Replaces RMSNorm::forward (use_quant = false) -> rms_norm
+ * (src/layernorm.cpp:20-24, kernels/layernorm_kernels.cu:6-34).                                          */
+int nb200_rms_norm(int dtype, const void *x, const void *weight, void *out, long long rows, int hidden, float eps, void *stream);
+
+/* out = a + b.  Replaces kernels::add (src/kernels/misc_kernels.cu:7-27).                                */
+int nb200_add(int dtype, const void *a, const void *b, void *out, long long numel, void *stream);
+
+/* In place, per batch b: x[b,i] = x[b,i] * (scale[b?, i % numel_scale] + scale_shift) + bias[b?, i % numel_bias]
+ * (scale == NULL: x += bias).  `numel` is per batch; a stride of 0 shares scale / bias across the batch.
+ * Replaces kernels::mul_add and kernels::mul_add_batch (src/kernels/misc_kernels.cu:29-131).               */
+int nb200_mul_add_batch(int dtype, void *x, const void *scale, const void *bias, float scale_shift, int batch, long long numel,
+                        long long numel_scale, long long numel_bias, long long stride_x, long long stride_scale,
+                        long long stride_bias, void *stream);
+
+/* De-interleave the last dim: outs[k][i] = input[i * n + k], n in 2..6.  Replaces kernels::split_mod<N>
+ * (src/kernels/misc_kernels.cu:187-214).                                                                */
+int nb200_split_mod(int dtype, const void *input, void *const *outs, int n, long long numel, void *stream);
+
+/* Element type conversion between fp16 / bf16 / fp32 (fp16 results clamp to +-65504).  Replaces kernels::cast
+ * (src/kernels/misc_kernels.cu:256-285).                                                                 */
+int nb200_cast(int dtype_in, const void *input, int dtype_out, void *output, long long numel, void *stream);
 
 /* Number of kernels the last nb200_* call on this thread launched (bench bookkeeping). */
 int nb200_last_launch_count(void);

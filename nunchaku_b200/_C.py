@@ -16,7 +16,7 @@ NB200_MAX_LORA_SCALES = 64
 NB200_FP16, NB200_BF16 = 0, 1
 NB200_ACT_NONE, NB200_ACT_SILU, NB200_ACT_GELU = 0, 1, 2
 
-c_void_p, c_int, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+c_void_p, c_int, c_float, c_longlong = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
 
 
 class QuantizeArgs(ctypes.Structure):
@@ -92,6 +92,14 @@ SYMBOLS = {
     "nb200_quantize_workspace_bytes": (ctypes.c_longlong, [c_int, c_int]),
     "nb200_quantize_w4a4_act_fuse_lora": (c_int, [ctypes.POINTER(QuantizeArgs), c_void_p]),
     "nb200_gemm_w4a4": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "nb200_activation": (c_int, [c_int, c_int, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "nb200_layernorm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
+    "nb200_rms_norm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
+    "nb200_add": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    "nb200_mul_add_batch": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_longlong, c_longlong, c_longlong,
+                                    c_longlong, c_longlong, c_longlong, c_void_p]),
+    "nb200_split_mod": (c_int, [c_int, c_void_p, ctypes.POINTER(c_void_p), c_int, c_longlong, c_void_p]),
+    "nb200_cast": (c_int, [c_int, c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
 }
 
 
