@@ -14,8 +14,9 @@ def test_activations_close_to_fp64(dtype):
     silu = xs / (1 + torch.exp(-xs))
     assert ((O.silu(x).double() - silu).abs() <= eps * silu.abs() + 1e-7).all()
     gelu = torch.nn.functional.gelu(xs, approximate="tanh")
-    # gelu_new rounds x^3, the tanh argument and tanh itself to T: a few ulp of T overall
-    assert ((O.gelu_new(x).double() - gelu).abs() <= 6 * eps * gelu.abs().clamp_min(0.05)).all()
+    # gelu_new rounds x^3, the tanh argument, tanh and (1 + tanh) to T: the error is absolute, ~eps * |x|
+    # (in the negative tail 1 + T(tanh) cancels to 0 -- that IS the reference's behaviour)
+    assert ((O.gelu_new(x).double() - gelu).abs() <= 2 * eps * xs.abs().clamp_min(1.0)).all()
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
