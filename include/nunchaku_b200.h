@@ -159,6 +159,14 @@ typedef struct nb200_gemm_args {
     int block_n;           /* 128 / 256: single-CTA tiles; 512: CTA-pair (cta_group::2) 256x256 tiles      */
     int num_sms;
     void *prof;            /* optional device buffer, 16 x int64 per CTA: barrier-wait cycle counters  */
+    /* rotary mode, optional: attention-ready Q / K / V instead of `out` (EpiloguePackQKV,
+     * src/kernels/zgemm/epilogues.cuh:427-550; wiring gemm_w4a4_launch_impl.cuh:376-393).
+     * fp16 [heads, rows >= Mp, 128] each, row pitch 128, head pitch stride_head_* elements; element order is
+     * plain row-major (the reference writes its own attention kernel's fragment order).  Rows >= attn_tokens are
+     * filled with 0 (Q, V) / NaN (K) exactly like the reference's mask (epilogues.cuh:479-489, 539-545).       */
+    void *out_q, *out_k, *out_v;
+    long long stride_head_q, stride_head_k, stride_head_v;
+    int attn_tokens;
 } nb200_gemm_args;
 
 int nb200_gemm_w4a4(const nb200_gemm_args *args, void *stream);

@@ -73,6 +73,13 @@ class GemmArgs(ctypes.Structure):
         ("block_n", c_int),
         ("num_sms", c_int),
         ("prof", c_void_p),
+        ("out_q", c_void_p),
+        ("out_k", c_void_p),
+        ("out_v", c_void_p),
+        ("stride_head_q", c_longlong),
+        ("stride_head_k", c_longlong),
+        ("stride_head_v", c_longlong),
+        ("attn_tokens", c_int),
     ]
 
 

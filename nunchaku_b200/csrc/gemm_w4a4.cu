@@ -69,6 +69,9 @@ struct GemmParams {
     // EPI_ROPE
     const void *norm_q, *norm_k;  // hT [128]
     const float *rotary;          // reference pack_rotemb layout [Mp][128]
+    __half *out_qkv[3];           // EpiloguePackQKV: fp16 [heads][rows][128] each (null: store `out`)
+    long long stride_head[3];
+    int attn_tokens;
     long long *prof;              // optional [grid][16] cycle counters (tools/gemm_prof.py)
     int debug;                    // NB200_GEMM_DEBUG experiment bits (results invalid when non-zero): 1 = converters
                                   // skip their smem stores, 2 = converters skip all work, 4 = no main-loop MMAs, 8 = epilogue drains TMEM but skips math/stores
@@ -465,11 +468,14 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
 
             // ---- EPI_ROPE pass 1: per-row sum of squares over the 128-wide head (epilogues.cuh:327-341)
             [[maybe_unused]] bool do_rope = false;
+            [[maybe_unused]] int qkv_part = 0, qkv_head = 0;
             [[maybe_unused]] float rope_coef = 1.f;
             [[maybe_unused]] const float *normw = s.aux;
             [[maybe_unused]] const float *rot_row = nullptr;
             if constexpr (EPI == EPI_ROPE) {
                 const int part = nb / (p.num_n_blocks / 3);  // 0 = Q heads, 1 = K heads, 2 = V (untouched)
+                qkv_part = part;
+                qkv_head = nb % (p.num_n_blocks / 3);
                 do_rope = part < 2;
                 if (do_rope) {
                     float sumsq = 0.f;
@@ -512,7 +518,9 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             auto do_chunk = [&](const int ch, const uint32_t (&v0)[32], const uint32_t (&v1)[32]) {
                 // staging buffer: one group -> two buffers alternate; two groups -> one buffer each
                 const int buf = H == 2 ? h : (store_count & 1);
-                if (et == 0) {
+                [[maybe_unused]] bool pack_qkv = false;
+                if constexpr (EPI == EPI_ROPE) pack_qkv = p.out_qkv[0] != nullptr;
+                if (et == 0 && !pack_qkv) {
                     if constexpr (H == 2)
                         bulk_wait_group_read<0>();
                     else
@@ -521,8 +529,17 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 if constexpr (EPI == EPI_QUANT) {
                     if (p.R_down > 0) mbar_wait(&s.stage_mma_done[buf], smd_phase[buf] ^ 1);
                 }
-                named_bar_sync(2 + 2 * h, kNumEpiThreads);
+                if (!pack_qkv) named_bar_sync(2 + 2 * h, kNumEpiThreads);
                 uint8_t *srow = s.out_stage[buf] + row * 128;
+                // EpiloguePackQKV (epilogues.cuh:427-550): this thread's row of the head, 64 fp16 of this chunk
+                [[maybe_unused]] __half *qkv_row = nullptr;
+                [[maybe_unused]] bool qkv_masked = false;
+                if constexpr (EPI == EPI_ROPE) {
+                    if (pack_qkv) {
+                        qkv_row = p.out_qkv[qkv_part] + qkv_head * p.stride_head[qkv_part] + static_cast<size_t>(m0 + row) * 128 + ch * 64;
+                        qkv_masked = m0 + row >= p.attn_tokens;
+                    }
+                }
                 [[maybe_unused]] uint32_t gw[32];  // EPI_QUANT: the 64 hT values of this row/chunk
 #pragma unroll
                 for (int c8 = 0; c8 < 8; c8++) {
@@ -570,8 +587,26 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         typename Tr::T2 h = Tr::from_float2(make_float2(y0, y1));
                         w[i] = *reinterpret_cast<uint32_t *>(&h);
                         if constexpr (EPI == EPI_QUANT) gw[c8 * 4 + i] = w[i];
+                        if constexpr (EPI == EPI_ROPE) {
+                            if (pack_qkv) {  // hT -> fp16 through fp32 (convert_half2, epilogues.cuh:446-453); pad rows masked
+                                const __half2 hh = __float22half2_rn(Tr::to_float2(h));
+                                w[i] = qkv_masked ? (qkv_part == 1 ? 0x7FFF7FFFu : 0u) : *reinterpret_cast<const uint32_t *>(&hh);
+                            }
+                        }
+                    }
+                    if constexpr (EPI == EPI_ROPE) {
+                        if (pack_qkv) {
+                            *reinterpret_cast<uint4 *>(qkv_row + c8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                            continue;
+                        }
                     }
                     *reinterpret_cast<uint4 *>(srow + ((c8 ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                if constexpr (EPI == EPI_ROPE) {
+                    if (pack_qkv) {
+                        store_count++;
+                        return;
+                    }
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(3 + 2 * h, kNumEpiThreads);
@@ -875,6 +910,13 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.norm_q = a.norm_q;
     p.norm_k = a.norm_k;
     p.rotary = a.rotary_emb;
+    p.out_qkv[0] = static_cast<__half *>(a.out_q);
+    p.out_qkv[1] = static_cast<__half *>(a.out_k);
+    p.out_qkv[2] = static_cast<__half *>(a.out_v);
+    p.stride_head[0] = a.stride_head_q;
+    p.stride_head[1] = a.stride_head_k;
+    p.stride_head[2] = a.stride_head_v;
+    p.attn_tokens = a.attn_tokens;
     for (int i = 0; i < NB200_MAX_LORA_SCALES; i++) p.lora_scales[i] = a.lora_scales[i];
 
     static int num_sms_cached = 0;
@@ -931,7 +973,7 @@ extern "C" __attribute__((visibility("default"))) int nb200_gemm_w4a4(const nb20
     NB200_REQUIRE(a->R_up >= 0 && a->R_up % 16 == 0, "R_up must be a multiple of 16");
     NB200_REQUIRE((a->R_up == 0) || (a->lora_act_in && a->lora_up), "lora_act_in and lora_up go together");
     NB200_REQUIRE(a->R_up <= 16 * NB200_MAX_LORA_SCALES, "rank exceeds MAX_RANK (1024)");
-    NB200_REQUIRE(a->out != nullptr || a->qout != nullptr, "out or qout must be non-NULL");
+    NB200_REQUIRE(a->out != nullptr || a->qout != nullptr || a->out_q != nullptr, "out, qout or out_q must be non-NULL");
     if (a->qout != nullptr) {
         // fc1 -> GELU -> (lora_down of fc2) -> quantise for fc2   (launch_impl:282-310)
         NB200_REQUIRE(a->oscales && a->smooth_next, "qout needs oscales and smooth_next");
@@ -943,8 +985,20 @@ extern "C" __attribute__((visibility("default"))) int nb200_gemm_w4a4(const nb20
         NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->qout) & 15) == 0, "qout must be 16-byte aligned");
     }
     if (a->rotary_emb != nullptr) {
-        NB200_REQUIRE(a->norm_q && a->norm_k && a->out, "rotary_emb needs norm_q, norm_k and out");
+        NB200_REQUIRE(a->norm_q && a->norm_k && (a->out || a->out_q), "rotary_emb needs norm_q, norm_k and out (or out_q/k/v)");
         NB200_REQUIRE(a->N % 384 == 0, "RMSNorm+RoPE epilogue: N must be 3 * heads * 128");
+    }
+    if (a->out_q != nullptr || a->out_k != nullptr || a->out_v != nullptr) {
+        NB200_REQUIRE(a->rotary_emb != nullptr, "out_q/out_k/out_v are outputs of the RMSNorm+RoPE epilogue (launch_impl:376)");
+        NB200_REQUIRE(a->out_q && a->out_k && a->out_v, "out_q, out_k and out_v go together");
+        NB200_REQUIRE(a->out == nullptr, "out and out_q/k/v are exclusive (launch_impl:376-405)");
+        NB200_REQUIRE(a->attn_tokens >= 0 && a->attn_tokens <= a->Mp, "attn_tokens must be in [0, Mp]");
+        NB200_REQUIRE(a->stride_head_q >= static_cast<long long>(a->Mp) * 128 && a->stride_head_k >= static_cast<long long>(a->Mp) * 128 &&
+                          a->stride_head_v >= static_cast<long long>(a->Mp) * 128,
+                      "head pitch must cover Mp rows of 128");
+        NB200_REQUIRE(((reinterpret_cast<uintptr_t>(a->out_q) | reinterpret_cast<uintptr_t>(a->out_k) | reinterpret_cast<uintptr_t>(a->out_v)) & 15) == 0 &&
+                          a->stride_head_q % 8 == 0 && a->stride_head_k % 8 == 0 && a->stride_head_v % 8 == 0,
+                      "out_q/k/v must be 16-byte aligned");
     }
     if (a->out != nullptr) {
         NB200_REQUIRE(a->M_out > 0 && a->M_out <= a->Mp && a->Mp - a->M_out < 256, "M_out must be in (Mp-256, Mp]");

@@ -60,7 +60,29 @@ def fused_qkv_norm_rottary(
     x = x.view(batch_size * seq_len, channels)
     quantized_x, ascales, lora_act = proj.quantize(x)
     if isinstance(output, tuple):
-        raise NotImplementedError("PackQKV outputs (nunchaku-fp16 attention layout) are not built yet")
+        # attention-ready fp16 Q / K / V, [1, heads, tokens_pad, 128] each (nunchaku/ops/fused.py:137-159)
+        assert len(output) == 3
+        output_q, output_k, output_v = output
+        svdq_gemm_w4a4_cuda(
+            act=quantized_x,
+            wgt=proj.qweight,
+            ascales=ascales,
+            wscales=proj.wscales,
+            lora_act_in=lora_act,
+            lora_up=proj.proj_up,
+            bias=proj.bias,
+            fp4=proj.precision == "nvfp4",
+            alpha=proj.wtscale,
+            wcscales=proj.wcscales,
+            norm_q=norm_q.weight if norm_q is not None else None,
+            norm_k=norm_k.weight if norm_k is not None else None,
+            rotary_emb=rotary_emb,
+            out_q=output_q,
+            out_k=output_k,
+            out_v=output_v,
+            attn_tokens=attn_tokens,
+        )
+        return output_q, output_k, output_v
     if output is None:
         output = torch.empty(batch_size * seq_len, proj.out_features, dtype=x.dtype, device=x.device)
     svdq_gemm_w4a4_cuda(

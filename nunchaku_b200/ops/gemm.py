@@ -61,13 +61,25 @@ def svdq_gemm_w4a4_cuda(
         raise RuntimeError("nunchaku_b200 has no CPU path: act must be a CUDA tensor")
     if out_vk is not None or out_linearattn is not None:
         raise NotImplementedError("SANA LiteLA epilogue (out_vk/out_linearattn) is not built yet")
-    if out_q is not None or out_k is not None or out_v is not None:
-        raise NotImplementedError("PackQKV epilogue (out_q/out_k/out_v) is not built yet")
+    pack_qkv = out_q is not None or out_k is not None or out_v is not None
+    if pack_qkv:
+        # EpiloguePackQKV (launch_impl:376-393): fp16 [B=1, heads, rows >= Mp, 128], plain row-major inside a head
+        if out_q is None or out_k is None or out_v is None:
+            raise ValueError("out_q, out_k and out_v go together")
+        if rotary_emb is None:
+            raise ValueError("out_q/out_k/out_v need rotary_emb, norm_q and norm_k (launch_impl:347-376)")
+        for t in (out_q, out_k, out_v):
+            if t.dtype != torch.float16 or t.dim() != 4 or t.shape[0] != 1 or t.shape[-1] != 128:
+                raise ValueError("out_q/out_k/out_v must be float16 [1, heads, tokens_pad, 128]")
+            if t.stride(-1) != 1 or t.stride(-2) != 128:
+                raise ValueError("out_q/out_k/out_v: the last two dims must be contiguous")
     fused_quant = qout is not None and oscales is not None          # launch_impl:282
     if (qout is None) != (oscales is None):
         raise ValueError("qout and oscales go together")
-    if out is None and not fused_quant:
-        raise ValueError("out is required unless qout/oscales are given")
+    if out is None and not fused_quant and not pack_qkv:
+        raise ValueError("out is required unless qout/oscales or out_q/out_k/out_v are given")
+    if pack_qkv:
+        out = None  # the reference ignores `out` in this mode (launch_impl:376-393)
     if fused_quant and smooth_factor is None:
         raise ValueError("qout needs smooth_factor (the next layer's smoothing vector)")
     if (lora_down is None) != (lora_act_out is None):
@@ -87,7 +99,12 @@ def svdq_gemm_w4a4_cuda(
     if wgt.shape[1] * 2 != K:
         raise ValueError("act and wgt disagree on K")
     out2d = None if out is None else out.view(-1, out.shape[-1])
-    dtype = out.dtype if out is not None else (bias.dtype if bias is not None else lora_up.dtype)
+    if out is not None:
+        dtype = out.dtype
+    elif not fp4:
+        dtype = ascales.dtype            # gemm_w4a4.cu:63-73: INT4 infers the 16-bit type from ascales
+    else:
+        dtype = bias.dtype if bias is not None else (lora_up.dtype if lora_up is not None else norm_q.dtype)
 
     args = GemmArgs()
     args.act = act.data_ptr()
@@ -136,6 +153,14 @@ def svdq_gemm_w4a4_cuda(
         args.rotary_emb = rotary_emb.data_ptr()
         args.norm_q = norm_q.contiguous().data_ptr()
         args.norm_k = norm_k.contiguous().data_ptr()
+        if pack_qkv:
+            heads = N // 384
+            for t in (out_q, out_k, out_v):
+                if t.shape[1] != heads or t.shape[2] < Mp:
+                    raise ValueError(f"out_q/out_k/out_v must hold {heads} heads of >= {Mp} rows")
+            args.out_q, args.out_k, args.out_v = out_q.data_ptr(), out_k.data_ptr(), out_v.data_ptr()
+            args.stride_head_q, args.stride_head_k, args.stride_head_v = out_q.stride(1), out_k.stride(1), out_v.stride(1)
+            args.attn_tokens = int(attn_tokens)
     args.dtype = torch_dtype_code(dtype)
     args.fp4 = int(fp4)
     args.act_unsigned = int(act_unsigned)

@@ -179,3 +179,49 @@ def test_qkv_rmsnorm_rope(fp4, hT):
     kw.pop("rope")
     v_ex = O.gemm_w4a4(mode="exact", **kw).out[:, 2 * N // 3:]
     assert O.rel_fro(out.cpu()[:, 2 * N // 3:], v_ex) <= (4e-3 if hT == torch.bfloat16 else 1.5e-3)
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+def test_qkv_pack_outputs(fp4, hT):
+    """EpiloguePackQKV (epilogues.cuh:427-550): the RMSNorm+RoPE result delivered as three fp16 [1, H, Tpad, 128]
+    tensors.  Bit-exact against the same kernel's row-major `out` (converted hT -> fp32 -> fp16 like
+    convert_half2); pad rows (>= attn_tokens) are 0 for Q / V and NaN for K; memory outside the views is untouched.
+    The element order inside a head is plain row-major (ours), not the reference attention kernel's fragment order."""
+    from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
+
+    H, K, R, M = 2, 256, 32, 300
+    N = 3 * H * 128
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=81)
+    g = torch.Generator().manual_seed(82)
+    norm_q = (1.0 + 0.2 * torch.randn(128, generator=g)).to(hT)
+    norm_k = (1.0 + 0.2 * torch.randn(128, generator=g)).to(hT)
+    x = O.make_activations(M, K, hT, seed=83, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=fp4)
+    Mp = qa.q.shape[0]
+    ang = torch.rand(Mp, 64, generator=g) * 6.283
+    rot = F.pack_rotemb(torch.sin(ang), torch.cos(ang)).cuda()
+    params = ref_layout_params(layer)
+    act, asc = _pack_act(qa, fp4, hT)
+    common = dict(act=act, wgt=params["qweight"], ascales=asc, wscales=params["wscales"], lora_act_in=qa.lora_act.cuda(),
+                  lora_up=params["proj_up"], bias=params["bias"], fp4=fp4, alpha=layer.alpha, wcscales=params["wcscales"],
+                  norm_q=norm_q.cuda(), norm_k=norm_k.cuda(), rotary_emb=rot)
+    out = torch.empty(Mp, N, dtype=hT, device="cuda")
+    svdq_gemm_w4a4_cuda(out=out, **common)
+    # joint-block style: this stream's tokens live at rows [256, 256 + Mp) of a longer sequence
+    pad0 = 256
+    full = [torch.full((1, H, pad0 + Mp, 128), 7.0, dtype=torch.float16, device="cuda") for _ in range(3)]
+    views = [t[:, :, pad0:] for t in full]
+    svdq_gemm_w4a4_cuda(out_q=views[0], out_k=views[1], out_v=views[2], attn_tokens=M, **common)
+    torch.cuda.synchronize()
+    want = out.float().to(torch.float16).view(Mp, 3, H, 128).permute(1, 2, 0, 3).cpu()  # [3, H, Mp, 128]
+    for part, (t, v) in enumerate(zip(full, views)):
+        got = v[0].cpu()
+        assert torch.equal(got[:, :M].view(torch.int16), want[part][:, :M].view(torch.int16)), f"part {part}"
+        if part == 1:
+            assert torch.isnan(got[:, M:]).all()
+        else:
+            assert (got[:, M:] == 0).all()
+        assert (t[:, :, :pad0] == 7.0).all()
+    with pytest.raises(ValueError):
+        svdq_gemm_w4a4_cuda(out_q=views[0], out_k=views[1], out_v=None, attn_tokens=M, **common)

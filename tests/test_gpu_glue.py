@@ -5,7 +5,9 @@ Tolerances (written here as the task requires):
     rounded 16-bit ops; mul+add is one fused rounding on both sides, see oracle/glue.py).
   * silu, gelu_new: expf / tanhf are CUDA's fp32 library versions (<= 2 ulp fp32) vs glibc's on the CPU;
     after rounding to 16 bits at most a 1-ulp-of-T difference on a small fraction of elements.
-  * layernorm, rms_norm: fp32 row statistics summed in a different order -> 1 ulp of T.
+  * layernorm, rms_norm: fp32 row statistics summed in a different order: mean / rstd can differ in the last
+    fp32 bit, which moves an output by <= 1 ulp of T (layernorm; ulp taken at max(|y|, 2^-6) because
+    (x - mean) cancels near zero) or <= 2 ulp of T (rms_norm rounds T(x * rstd) and then T(n * w)).
 """
 import pytest
 import torch
@@ -15,17 +17,17 @@ pytestmark = pytest.mark.gpu
 DTYPES = [torch.bfloat16, torch.float16]
 
 
-def _ulp_diff(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """|a - b| in units of the larger operand's ulp (16-bit types)."""
+def _ulp_diff(a: torch.Tensor, b: torch.Tensor, floor: float = 0.0) -> torch.Tensor:
+    """|a - b| in units of the larger operand's ulp (16-bit types); magnitudes below `floor` use floor's ulp."""
     bits = 7 if a.dtype == torch.bfloat16 else 10
     af, bf = a.double().cpu(), b.double().cpu()
-    mag = torch.maximum(af.abs(), bf.abs()).clamp_min(2.0 ** -14 if a.dtype == torch.float16 else 2.0 ** -126)
+    mag = torch.maximum(af.abs(), bf.abs()).clamp_min(max(floor, 2.0 ** -14 if a.dtype == torch.float16 else 2.0 ** -126))
     ulp = torch.exp2(torch.floor(torch.log2(mag)) - bits)
     return (af - bf).abs() / ulp
 
 
-def _assert_ulp(got, want, max_ulp=1.0, max_frac=0.02):
-    d = _ulp_diff(got, want)
+def _assert_ulp(got, want, max_ulp=1.0, max_frac=0.02, floor=0.0):
+    d = _ulp_diff(got, want, floor)
     assert d.max().item() <= max_ulp, f"max diff {d.max().item()} ulp"
     assert (d > 0).double().mean().item() <= max_frac, f"{(d > 0).double().mean().item():.4f} of elements differ"
 
@@ -61,7 +63,7 @@ def test_layernorm(dtype, rows, hidden, affine):
     w = (1 + 0.1 * torch.randn(hidden, generator=g)).to(dtype) if affine else None
     b = (0.1 * torch.randn(hidden, generator=g)).to(dtype) if affine else None
     got = glue.layernorm(x.cuda(), None if w is None else w.cuda(), None if b is None else b.cuda(), 1e-6)
-    _assert_ulp(got, O.layernorm(x, w, b, 1e-6), max_frac=0.05)
+    _assert_ulp(got, O.layernorm(x, w, b, 1e-6), max_frac=0.05, floor=2.0 ** -6)
     # independent check against torch's own fp32 layer_norm
     ref = torch.nn.functional.layer_norm(x.float(), (hidden,), None if w is None else w.float(), None if b is None else b.float(), 1e-6)
     assert (got.float().cpu() - ref).abs().max().item() <= 2.0 ** (-7 if dtype == torch.bfloat16 else -10) * max(1.0, ref.abs().max().item())
@@ -76,7 +78,7 @@ def test_rms_norm(dtype, rows, hidden):
     g = torch.Generator().manual_seed(2)
     x = torch.randn(rows, hidden, generator=g).to(dtype)
     w = (1 + 0.1 * torch.randn(hidden, generator=g)).to(dtype)
-    _assert_ulp(glue.rms_norm(x.cuda(), w.cuda(), 1e-6), O.rms_norm(x, w, 1e-6), max_frac=0.05)
+    _assert_ulp(glue.rms_norm(x.cuda(), w.cuda(), 1e-6), O.rms_norm(x, w, 1e-6), max_ulp=2.0, max_frac=0.05)
 
 
 @pytest.mark.parametrize("dtype", DTYPES + [torch.float32])
