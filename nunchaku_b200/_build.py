@@ -79,7 +79,27 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
     os.replace(tmp, LIB_PATH)
+    build_cpp_twin_driver()
     return LIB_PATH
+
+
+TWIN_DRIVER = os.path.join(LIB_DIR, "linear_twin_main")
+
+
+def build_cpp_twin_driver() -> str:
+    """g++ build of the C++ twin's test driver (tests/cpp/linear_twin_main.cpp) against the shared library;
+    the binary lives next to the .so so that it travels to the GPU box with it."""
+    src = os.path.join(os.path.dirname(PKG_DIR), "tests", "cpp", "linear_twin_main.cpp")
+    if not os.path.exists(src):
+        return ""
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-O2", "-std=c++17", "-I", INCLUDE, "-I", os.path.join(cuda, "include"), src, "-o", TWIN_DRIVER,
+           "-L", LIB_DIR, "-lnunchaku_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath,$ORIGIN",
+           "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"g++ failed for {src}:\n{res.stdout}")
+    return TWIN_DRIVER
 
 
 if __name__ == "__main__":

@@ -294,6 +294,74 @@ norm_kernel(const T *__restrict__ x, const T *__restrict__ gamma, const T *__res
     for (int j = CHUNKS * kThreads + threadIdx.x; j < nvec; j += kThreads) apply(reinterpret_cast<const Vec<T, V> *>(xr)[j], j);
 }
 
+// Rows up to 4096 elements (every norm on the FLUX / SANA path): ONE WARP per row, the row lives in registers,
+// statistics by xor-shuffle only -- no shared memory, no __syncthreads, ~6 KB of loads in flight per warp.
+template <typename T, bool RMS, int MAXC>
+__global__ void __launch_bounds__(kThreads)
+norm_warp_kernel(const T *__restrict__ x, const T *__restrict__ gamma, const T *__restrict__ beta, T *__restrict__ out,
+                 long long rows, int hidden, float eps) {
+    constexpr int V = 8;
+    const int lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T *xr = x + row * hidden;
+    T *orow = out + row * hidden;
+    const int nvec = hidden / V;
+    Vec<T, V> reg[MAXC];
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+        const int j = c * 32 + lane;
+        if (j < nvec) reg[c] = reinterpret_cast<const Vec<T, V> *>(xr)[j];
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+        const int j = c * 32 + lane;
+        if (j < nvec) {
+#pragma unroll
+            for (int k = 0; k < V; k++) {
+                const float f = to_f(reg[c].v[k]);
+                s0 += f;
+                s1 = fmaf(f, f, s1);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    float mean = 0.f, rstd;
+    if constexpr (RMS) {
+        rstd = rsqrtf(s1 / hidden + eps);
+    } else {
+        mean = s0 / hidden;
+        rstd = rsqrtf(s1 / hidden - mean * mean + eps);
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; c++) {
+        const int j = c * 32 + lane;
+        if (j < nvec) {
+            Vec<T, V> a = reg[c], g, b;
+            if (gamma != nullptr) g = reinterpret_cast<const Vec<T, V> *>(gamma)[j];
+            if (!RMS && beta != nullptr) b = reinterpret_cast<const Vec<T, V> *>(beta)[j];
+#pragma unroll
+            for (int k = 0; k < V; k++) {
+                if constexpr (RMS) {
+                    const T n = from_f<T>(to_f(a.v[k]) * rstd);
+                    a.v[k] = gamma != nullptr ? t_mul(n, g.v[k]) : n;
+                } else {
+                    float r = (to_f(a.v[k]) - mean) * rstd;
+                    if (gamma != nullptr) r = r * to_f(g.v[k]);
+                    if (beta != nullptr) r = r + to_f(b.v[k]);
+                    a.v[k] = from_f<T>(r);
+                }
+            }
+            reinterpret_cast<Vec<T, V> *>(orow)[j] = a;
+        }
+    }
+}
+
 int grid_for(long long nvec) {
     long long g = (nvec + kThreads - 1) / kThreads;
     const long long cap = 148LL * 16;  // grid-stride beyond 16 resident CTAs per SM
@@ -460,6 +528,28 @@ static int launch_norm(bool rms, int dtype, const void *x, const void *weight, c
         } else {
             const T *xp = static_cast<const T *>(x), *g = static_cast<const T *>(weight), *b = static_cast<const T *>(bias);
             T *o = static_cast<T *>(out);
+            if (hidden <= 4096) {
+                const int wgrid = static_cast<int>((rows + kThreads / 32 - 1) / (kThreads / 32));
+                const int wc = (hidden / 8 + 31) / 32;
+#define NB200_NORMW(RMS, C) norm_warp_kernel<T, RMS, C><<<wgrid, kThreads, 0, stream>>>(xp, g, b, o, rows, hidden, eps)
+                if (rms) {
+                    if (wc <= 1) NB200_NORMW(true, 1);
+                    else if (wc <= 4) NB200_NORMW(true, 4);
+                    else if (wc <= 8) NB200_NORMW(true, 8);
+                    else if (wc <= 12) NB200_NORMW(true, 12);
+                    else NB200_NORMW(true, 16);
+                } else {
+                    if (wc <= 1) NB200_NORMW(false, 1);
+                    else if (wc <= 4) NB200_NORMW(false, 4);
+                    else if (wc <= 8) NB200_NORMW(false, 8);
+                    else if (wc <= 12) NB200_NORMW(false, 12);
+                    else NB200_NORMW(false, 16);
+                }
+#undef NB200_NORMW
+                NB200_CUDA_CHECK(cudaGetLastError());
+                count_launch();
+                return NB200_OK;
+            }
             const int grid = static_cast<int>(rows);
             const int chunks = (hidden / 8 + kThreads - 1) / kThreads;
 #define NB200_NORM(RMS, C) norm_kernel<T, RMS, C><<<grid, kThreads, 0, stream>>>(xp, g, b, o, hidden, eps)
