@@ -1,5 +1,5 @@
 """Row a4: the C++ twin of the module (include/nunchaku_b200_linear.hpp, class GEMM_W4A4 mirroring
-src/Linear.h:53-120) must produce bit-identical results to the Python mirror (SVDQW4A4Linear) on the same
+src/Linear.h:53-120) must produce identical results (bit-identical wherever the kernels are run-to-run deterministic) to the Python mirror (SVDQW4A4Linear) on the same
 checkpoint bytes: both sit on the same C ABI, so any difference is a host-side wiring bug (padding, repack
 arguments, unsigned flag of the fused GELU->quantise hand-off, lora scales ...)."""
 import os
@@ -95,5 +95,10 @@ def test_cpp_twin_matches_python_mirror(precision, hT, tmp_path):
                         bias=fc1.bias, fp4=fp4, alpha=fc1.wtscale, wcscales=fc1.wcscales, fuse_silu=True)
     y_mlp = fused_gelu_mlp(xd.view(1, M, D), fc1, fc2).view(M, D)
     torch.cuda.synchronize()
-    for name, want in (("y_plain", y_plain), ("y_silu", y_silu), ("y_mlp", y_mlp)):
+    for name, want in (("y_plain", y_plain), ("y_silu", y_silu)):
         assert torch.equal(got[name].view(torch.int16), want.cpu().view(torch.int16)), name
+    # the fused fc1 epilogue accumulates fc2's low-rank hidden state with fp32 atomics across the N tiles (as the
+    # reference does, lora.cuh:243-353 / SURVEY F8), so two RUNS of the same code agree only to fp32 summation order
+    a, b = got["y_mlp"].double(), y_mlp.cpu().double()
+    assert (a - b).norm() <= 2e-4 * b.norm(), "y_mlp"
+    assert (got["y_mlp"].view(torch.int16) != y_mlp.cpu().view(torch.int16)).double().mean() <= 0.02, "y_mlp"
