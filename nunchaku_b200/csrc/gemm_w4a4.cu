@@ -74,7 +74,8 @@ struct GemmParams {
     int attn_tokens;
     long long *prof;              // optional [grid][16] cycle counters (tools/gemm_prof.py)
     int debug;                    // NB200_GEMM_DEBUG experiment bits (results invalid when non-zero): 1 = converters
-                                  // skip their smem stores, 2 = converters skip all work, 4 = no main-loop MMAs, 8 = epilogue drains TMEM but skips math/stores
+                                  // skip their smem stores, 2 = converters skip all work, 4 = no main-loop MMAs, 8 = epilogue drains TMEM but skips math/stores,
+                                  // 16 = EPI_QUANT: skip the lora_act_out atomics, 32 = EPI_QUANT: skip the next-layer quantise math
     float lora_scales[NB200_MAX_LORA_SCALES];
 };
 
@@ -641,6 +642,10 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 }
                 if constexpr (EPI == EPI_QUANT) {
                     smd_phase[buf] ^= 1;
+                    if (p.debug & 32) {
+                        store_count++;
+                        return;
+                    }
                     // ---- next-layer quantisation of (gelu + shift) / smooth  (gemm_w4a4.cuh:930-1043) ---------
                     const int m = m0 + row;
                     uint8_t *qrow = p.qout + static_cast<size_t>(m) * (p.N >> 1) + ((n0 + ch * 64) >> 1);
@@ -767,7 +772,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; i++)
-                            if (c16 * 16 + i < p.R_down) atomicAdd(dst + c16 * 16 + i, __uint_as_float(d2[i]));
+                            if (c16 * 16 + i < p.R_down && !(p.debug & 16)) atomicAdd(dst + c16 * 16 + i, __uint_as_float(d2[i]));
                     }
                     tc_fence_before_sync();
                 }

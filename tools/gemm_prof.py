@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--K", type=int, default=3072)
     ap.add_argument("--N", type=int, default=3072)
     ap.add_argument("--bn", default="0,512")
+    ap.add_argument("--fused", action="store_true", help="profile the fc1 -> GELU -> quantise-for-fc2 epilogue (EPI_QUANT)")
     args = ap.parse_args()
     from nunchaku_b200.ops import gemm as G
 
@@ -36,17 +37,30 @@ def main():
         x = torch.randn(args.M, args.K, generator=g, device=dev).to(torch.bfloat16)
         q, s, la = m.quantize(x)
         out = torch.empty(args.M, args.N, dtype=torch.bfloat16, device=dev)
+        run = lambda: m.forward_quant(q, s, la, out)  # noqa: E731
+        if args.fused:
+            fp4 = prec == "nvfp4"
+            m2 = make_layer(args.N, args.K, 32, prec, torch.bfloat16, dev, g)
+            Mp = q.shape[0]
+            q2 = torch.empty(Mp, args.N // 2, dtype=torch.uint8, device=dev)
+            s2 = (torch.empty(args.N // 16, Mp, dtype=torch.float8_e4m3fn, device=dev) if fp4
+                  else torch.empty(args.N // 64, Mp, dtype=torch.bfloat16, device=dev))
+            la2 = torch.empty(Mp, 32, dtype=torch.float32, device=dev)
+            run = lambda: G.svdq_gemm_w4a4_cuda(  # noqa: E731
+                act=q, wgt=m.qweight, qout=q2, ascales=s, wscales=m.wscales, oscales=s2, lora_act_in=la, lora_up=m.proj_up,
+                lora_down=m2.proj_down, lora_act_out=la2, bias=m.bias, smooth_factor=m2.smooth_factor, fp4=fp4, alpha=m.wtscale,
+                wcscales=m.wcscales)
         for bn in [int(b) for b in args.bn.split(",")]:
             G.BLOCK_N_OVERRIDE = bn
             for _ in range(3):
-                m.forward_quant(q, s, la, out)
+                run()
             prof = torch.zeros(148, 16, dtype=torch.int64, device=dev)
             G.PROF_BUFFER = prof
             torch.cuda.synchronize()
             torch.cuda._sleep(int(2e7))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            m.forward_quant(q, s, la, out)
+            run()
             e1.record()
             torch.cuda.synchronize()
             G.PROF_BUFFER = None
