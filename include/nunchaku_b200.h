@@ -205,6 +205,19 @@ int nb200_split_mod(int dtype, const void *input, void *const *outs, int n, long
  * (src/kernels/misc_kernels.cu:256-285).                                                                 */
 int nb200_cast(int dtype_in, const void *input, int dtype_out, void *output, long long numel, void *stream);
 
+/* ---- SANA linear attention ---------------------------------------------------
+ * Second half of the reference's EpilogueLiteLA (src/kernels/zgemm/epilogues.cuh:552-691, wiring
+ * gemm_w4a4_launch_impl.cuh:311-346), applied to the QKV projection's hT output qkv [batch, tokens, N],
+ * N = 3 * heads * 32 laid out [Q | per head: K(32) V(32)]:
+ *   out_q  [batch, tokens, N/3] hT   = relu(Q)
+ *   out_vk [batch, heads, 33, 32] f32: vk[v][k] = sum_t V[t,v] * relu(K[t,k]),  vk[32][k] = sum_t relu(K[t,k])
+ * out_vk is zero-filled inside the call (launch_impl:336) and accumulated with fp32 atomics.                */
+int nb200_litela_vk(int dtype, const void *qkv, void *out_q, float *out_vk, int batch, int tokens, int N, void *stream);
+
+/* In place: q[b,t,h,:] <- (q . vk[b,h,0..31,:]) / (q . vk[b,h,32,:] + eps), q hT [batch, tokens, heads, 32].
+ * Replaces kernels::linearattn_vk_mul_q (gemm_w4a4_launch_impl.cuh:427-448, epilogues.cuh:693-760; eps = 1e-6). */
+int nb200_linearattn_vk_mul_q(int dtype, void *q, const float *vk, int batch, int tokens, int heads, float eps, void *stream);
+
 /* Number of kernels the last nb200_* call on this thread launched (bench bookkeeping). */
 int nb200_last_launch_count(void);
 

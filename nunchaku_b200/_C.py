@@ -107,6 +107,8 @@ SYMBOLS = {
                                     c_longlong, c_longlong, c_longlong, c_void_p]),
     "nb200_split_mod": (c_int, [c_int, c_void_p, ctypes.POINTER(c_void_p), c_int, c_longlong, c_void_p]),
     "nb200_cast": (c_int, [c_int, c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
+    "nb200_litela_vk": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "nb200_linearattn_vk_mul_q": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
 }
 
 

@@ -66,6 +66,7 @@ struct GemmParams {
     const void *smooth_next; // hT [N]
     float *lora_act_out;     // [Mp][R_down], pre-zeroed
     int R_down, Rdp;
+    int tile_contig;         // 1: each CTA owns a contiguous range of tiles (same m-block runs), see EPI_QUANT
     // EPI_ROPE
     const void *norm_q, *norm_k;  // hT [128]
     const float *rotary;          // reference pack_rotemb layout [Mp][128]
@@ -219,6 +220,11 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     const int k64_total = p.K >> 6;
     const int num_kblocks = FP4 ? (k64_total + 3) >> 2 : k64_total;
     const int lora_chunks = p.lora_up != nullptr ? p.Rp / kLoraChunk : 0;
+    // tile schedule: round-robin (tile = cta + i * grid) or, for the fused down projection, one contiguous range per
+    // CTA so that consecutive tiles share the m-block and the projection keeps accumulating in TMEM
+    const int tile_begin = p.tile_contig ? static_cast<int>(static_cast<long long>(p.num_tiles) * blockIdx.x / gridDim.x) : blockIdx.x;
+    const int tile_end = p.tile_contig ? static_cast<int>(static_cast<long long>(p.num_tiles) * (blockIdx.x + 1) / gridDim.x) : p.num_tiles;
+    const int tile_step = p.tile_contig ? 1 : gridDim.x;
 
     // ---- one-time setup -----------------------------------------------------------------------
     if (warp == 0 && elect_one()) {
@@ -268,19 +274,9 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             uint32_t lora_phase = 0;
             uint32_t ld_phase = 0;
             long long t_empty = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 const int mb = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
                 const int m0 = mb * BM, n0 = nb * BN;
-                if constexpr (EPI == EPI_QUANT) {
-                    if (p.R_down > 0) {
-                        mbar_wait(&s.ld_b_empty, ld_phase ^ 1);
-                        mbar_expect_tx(&s.ld_b_full, (BN / 64) * p.Rdp * 128);
-#pragma unroll
-                        for (int ch = 0; ch < BN / 64; ch++)
-                            tma_load_2d(s.ld_b + ch * kMaxRdp * 128, &tm_ld, &s.ld_b_full, n0 + ch * 64, 0);
-                        ld_phase ^= 1;
-                    }
-                }
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     NB200_TIMED(t_empty, mbar_wait(&s.empty[st.idx], st.phase ^ 1));
                     if constexpr (FP4) {
@@ -315,6 +311,19 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                               BN * kLoraChunk * 2, &s.lora_b_full);
                     lora_phase ^= 1;
                 }
+                if constexpr (EPI == EPI_QUANT) {
+                    // next layer's lora_down slab: needed only by this tile's EPILOGUE, and its buffer is released by
+                    // the previous tile's epilogue -> fetch it after the main-loop stages are in flight, otherwise the
+                    // main loop of tile i+1 cannot start before the epilogue of tile i has finished
+                    if (p.R_down > 0) {
+                        mbar_wait(&s.ld_b_empty, ld_phase ^ 1);
+                        mbar_expect_tx(&s.ld_b_full, (BN / 64) * p.Rdp * 128);
+#pragma unroll
+                        for (int ch = 0; ch < BN / 64; ch++)
+                            tma_load_2d(s.ld_b + ch * kMaxRdp * 128, &tm_ld, &s.ld_b_full, n0 + ch * 64, 0);
+                        ld_phase ^= 1;
+                    }
+                }
             }
             if (p.prof) p.prof[blockIdx.x * 16 + 0] = t_empty;
         }
@@ -329,7 +338,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const long long t_mma0 = clock64();
             constexpr uint32_t idesc_main = FP4 ? make_idesc_nvf4(BM, BN) : make_idesc_f16(Tr::kIsBf16, BM, BN);
             constexpr uint32_t idesc_lora = make_idesc_f16(Tr::kIsBf16, BM, BN);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step, it++) {
                 const int acc = it % C::kNumAcc;
                 NB200_TIMED(t_tmem_empty, mbar_wait(&s.tmem_empty[acc], acc_phase[acc] ^ 1));
                 tc_fence_after_sync();
@@ -416,7 +425,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             for (int i = eta; i < 256; i += C::kEpiThreads)
                 s.aux[i] = Tr::to_float(reinterpret_cast<const hT *>(i < 128 ? p.norm_q : p.norm_k)[i & 127]);
         }
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, it++) {
+        for (int tile = tile_begin; tile < tile_end; tile += tile_step, it++) {
             const int mb = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
             const int m0 = mb * BM, n0 = nb * BN;
             const int acc = it % C::kNumAcc;
@@ -468,6 +477,9 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
             // ---- EPI_ROPE pass 1: per-row sum of squares over the 128-wide head (epilogues.cuh:327-341)
+            // fused down projection: D2 keeps accumulating in TMEM while consecutive tiles stay in the same m-block
+            [[maybe_unused]] const bool d2_fresh = tile == tile_begin || (tile - tile_step) / p.num_n_blocks != mb;
+            [[maybe_unused]] const bool d2_flush = tile + tile_step >= tile_end || (tile + tile_step) / p.num_n_blocks != mb;
             [[maybe_unused]] bool do_rope = false;
             [[maybe_unused]] int qkv_part = 0, qkv_head = 0;
             [[maybe_unused]] float rope_coef = 1.f;
@@ -632,7 +644,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 4; j++)
                                 tc_mma_f16(tmem_base + C::kTmemLd, make_sw128_kmajor_desc(a_addr + j * 32),
-                                           make_sw128_kmajor_desc(b_addr + j * 32), idesc_ld, (ch | j) != 0);
+                                           make_sw128_kmajor_desc(b_addr + j * 32), idesc_ld, (ch | j) != 0 || !d2_fresh);
                             tc_commit(&s.stage_mma_done[buf]);
                         }
                     }
@@ -758,23 +770,25 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             if constexpr (EPI == EPI_QUANT) {
                 if (p.R_down > 0) {
                     if (et == 0) {
-                        tc_commit(&s.d2_full);
+                        if (d2_flush) tc_commit(&s.d2_full);
                         tc_commit(&s.ld_b_empty);
                     }
-                    mbar_wait(&s.d2_full, d2_phase);
-                    d2_phase ^= 1;
-                    tc_fence_after_sync();
-                    float *dst = p.lora_act_out + static_cast<size_t>(m0 + row) * p.R_down;
-                    // two groups: each adds half of the 16-rank column blocks
-                    for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
-                        uint32_t d2[16];
-                        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kTmemLd + c16 * 16, d2);
-                        tmem_ld_wait();
+                    if (d2_flush) {  // last tile of this CTA's run in the m-block: add the partial projection to HBM
+                        mbar_wait(&s.d2_full, d2_phase);
+                        d2_phase ^= 1;
+                        tc_fence_after_sync();
+                        float *dst = p.lora_act_out + static_cast<size_t>(m0 + row) * p.R_down;
+                        // two groups: each adds half of the 16-rank column blocks
+                        for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
+                            uint32_t d2[16];
+                            tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kTmemLd + c16 * 16, d2);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; i++)
-                            if (c16 * 16 + i < p.R_down && !(p.debug & 16)) atomicAdd(dst + c16 * 16 + i, __uint_as_float(d2[i]));
+                            for (int i = 0; i < 16; i++)
+                                if (c16 * 16 + i < p.R_down && !(p.debug & 16)) atomicAdd(dst + c16 * 16 + i, __uint_as_float(d2[i]));
+                        }
+                        tc_fence_before_sync();
                     }
-                    tc_fence_before_sync();
                 }
             }
         }
@@ -804,7 +818,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             }
             const uint32_t offA = *reinterpret_cast<uint32_t *>(&offA2);
             const uint32_t offB = *reinterpret_cast<uint32_t *>(&offB2);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     NB200_TIMED(t_cfull, mbar_wait(&s.full[pst.idx], pst.phase));
                     NB200_TIMED(t_cempty, mbar_wait(&s.cempty[cst.idx], cst.phase ^ 1));
@@ -903,6 +917,7 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.mid_act = a.mid_act;
     p.act_unsigned = a.act_unsigned;
     p.prof = static_cast<long long *>(a.prof);
+    p.tile_contig = (EPI == EPI_QUANT && a.R_down > 0) ? 1 : 0;
     static const int dbg = getenv("NB200_GEMM_DEBUG") ? atoi(getenv("NB200_GEMM_DEBUG")) : 0;
     p.debug = dbg;
     p.out = a.out;

@@ -69,6 +69,18 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
                  : "r"(addr));
 }
 
+__device__ __forceinline__ float max_nan(float a, float b) {  // NaN-propagating max (fmaxf drops NaNs)
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 template <typename hT, bool FP4>
 __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
     using Tr = HalfTraits<hT>;
@@ -140,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                 // "if |b| < 2^-126 scale a and b by 2^24; MUFU.RCP(b) * a".  The reciprocal and the scale depend
                 // only on the column, so they are hoisted out of the 8 row passes of the tile.
                 float rsm[8], ksm[8];
+                bool any_tiny = false;
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     rsm[e] = 1.f;
@@ -155,11 +168,14 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
 #pragma unroll
                         for (int u = 0; u < 2; u++) {
                             const bool tiny = fabsf(bb[u]) < 1.175494350822287508e-38f;
+                            any_tiny |= tiny;
                             ksm[2 * e + u] = tiny ? 16777216.f : 1.f;
                             rsm[2 * e + u] = rcp_approx(tiny ? bb[u] * 16777216.f : bb[u]);
                         }
                     }
                 }
+                // denormal smoothing factors are the only case that needs the pre-scale (ksm); warp-uniform switch
+                const bool slow_div = __any_sync(0xffffffffu, any_tiny);
 
                 mbar_wait(&s.full[st], ph);
                 const uint32_t tile = smem_u32(s.tile[st]);
@@ -194,11 +210,16 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
 
                 // ---- smooth + quantise: 8 lanes per row, 4 rows per pass (gemm_w4a4.cuh:85-187,429-523) --
                 if (chunk == 0) {
-#pragma unroll 1
-                    for (int pass = 0; pass < kRows / 4; pass++) {
-                        const int r = pass * 4 + r4;
-                        const int m = row0 + r;
-                        const uint4 xv = *reinterpret_cast<const uint4 *>(s.tile[st] + r * 128 + ((c ^ (r & 7)) << 4));
+                    // per-lane constants of the tile: the lane's 16-byte chunk sits at (c ^ (r & 7)) of row r, and
+                    // r & 7 = (pass & 1) * 4 + r4 only depends on the pass parity
+                    const uint32_t tile_lane = tile + r4 * 128;
+                    const uint32_t sw0 = static_cast<uint32_t>((c ^ r4) << 4), sw1 = static_cast<uint32_t>((c ^ (4 + r4)) << 4);
+                    const size_t qpitch = static_cast<size_t>(p.K >> 1);
+                    uint8_t *qdst = p.q + static_cast<size_t>(row0 + r4) * qpitch + ((g * 64 + c * 8) >> 1);
+#pragma unroll 2
+                    for (int pass = 0; pass < kRows / 4; pass++, qdst += 4 * qpitch) {
+                        const int m = row0 + pass * 4 + r4;
+                        const uint4 xv = lds_v4(tile_lane + pass * 512 + ((pass & 1) ? sw1 : sw0));
                         const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
                         float xs[8];
                         float amax = 0.f;
@@ -206,26 +227,57 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                         for (int e = 0; e < 4; e++) {
                             float2 a = Tr::to_float2(*reinterpret_cast<const T2 *>(&xw[e]));
                             if (smooth != nullptr) {
-                                a.x = (a.x * ksm[2 * e]) * rsm[2 * e];
-                                a.y = (a.y * ksm[2 * e + 1]) * rsm[2 * e + 1];
+                                if (slow_div) {
+                                    a.x = (a.x * ksm[2 * e]) * rsm[2 * e];
+                                    a.y = (a.y * ksm[2 * e + 1]) * rsm[2 * e + 1];
+                                } else {  // ksm == 1: (a * 1) * rsm == a * rsm bit for bit
+                                    a.x = a.x * rsm[2 * e];
+                                    a.y = a.y * rsm[2 * e + 1];
+                                }
                                 a = Tr::to_float2(Tr::from_float2(a));   // h2div rounds the quotient to hT
                             }
                             xs[2 * e] = a.x;
                             xs[2 * e + 1] = a.y;
                             amax = fmaxf(amax, fmaxf(fabsf(a.x), fabsf(a.y)));
                         }
-                        uint8_t *qdst = p.q + static_cast<size_t>(m) * (p.K >> 1) + ((g * 64 + c * 8) >> 1);
                         if constexpr (!FP4) {
-                            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-                            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-                            const float s32 = amax * (1.0f / 7.0f);
-                            const float rs = rcp_approx_ftz(s32);
-                            if (c == 0) reinterpret_cast<hT *>(p.scales)[static_cast<size_t>(g) * p.Mp + m] = Tr::from_float(s32);
-                            int qv[8];
+                            // NaN-propagating absmax of the 64-wide group: NaN / inf / all-zero groups take the reference's
+                            // cvt.rni + saturating pack below (warp-uniform switch), everything else the magic-add pack
+                            float amax_p = max_nan(max_nan(max_nan(fabsf(xs[0]), fabsf(xs[1])), max_nan(fabsf(xs[2]), fabsf(xs[3]))),
+                                                   max_nan(max_nan(fabsf(xs[4]), fabsf(xs[5])), max_nan(fabsf(xs[6]), fabsf(xs[7]))));
+                            amax_p = max_nan(amax_p, __shfl_xor_sync(0xffffffffu, amax_p, 1));
+                            amax_p = max_nan(amax_p, __shfl_xor_sync(0xffffffffu, amax_p, 2));
+                            amax_p = max_nan(amax_p, __shfl_xor_sync(0xffffffffu, amax_p, 4));
+                            const bool regular = amax_p > 0.f && amax_p < 3.0e38f;
+                            if (__all_sync(0xffffffffu, regular)) {
+                                const float s32 = amax_p * (1.0f / 7.0f);
+                                const float rs = rcp_approx_ftz(s32);
+                                if (c == 0) reinterpret_cast<hT *>(p.scales)[static_cast<size_t>(g) * p.Mp + m] = Tr::from_float(s32);
+                                // cvt.rni + saturating s4 pack (gemm_utils.cuh:206-246) restated with a magic add: |x * rs| <= 7 + ulp,
+                                // so rn(x*rs) + (1.5 * 2^23 + 8) carries round-half-even(x*rs) + 8 in [1, 15] in its low mantissa
+                                // bits -- the same two roundings (mul, then to integer) as the reference, no saturation possible.
+                                // nibble p of the word = element 2p, nibble p + 4 = element 2p + 1  (offset binary, q + 8)
+                                uint32_t word = 0;
 #pragma unroll
-                            for (int e = 0; e < 8; e++) qv[e] = cvt_rni(xs[e] * rs);
-                            *reinterpret_cast<uint32_t *>(qdst) = pack8_int4_b200<false>(qv);
+                                for (int e = 0; e < 8; e++) {
+                                    const float f = __fadd_rn(__fmul_rn(xs[e], rs), 12582920.0f);
+                                    word += __float_as_uint(f) << (4 * ((e >> 1) + 4 * (e & 1)));   // upper bits cancel below
+                                }
+                                constexpr uint32_t kBias = 0x4B400000u + (0x4B400000u << 4) + (0x4B400000u << 8) + (0x4B400000u << 12) +
+                                                           (0x4B400000u << 16) + (0x4B400000u << 20) + (0x4B400000u << 24) + (0x4B400000u << 28);
+                                *reinterpret_cast<uint32_t *>(qdst) = word - kBias;
+                            } else {
+                                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                                const float s32 = amax * (1.0f / 7.0f);
+                                const float rs = rcp_approx_ftz(s32);
+                                if (c == 0) reinterpret_cast<hT *>(p.scales)[static_cast<size_t>(g) * p.Mp + m] = Tr::from_float(s32);
+                                int qv[8];
+#pragma unroll
+                                for (int e = 0; e < 8; e++) qv[e] = cvt_rni(xs[e] * rs);
+                                *reinterpret_cast<uint32_t *>(qdst) = pack8_int4_b200<false>(qv);
+                            }
                         } else {
                             amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));   // 16-group = chunk pair
                             const float sc = fminf(amax * (1.0f / 6.0f), 448.0f);
