@@ -59,8 +59,23 @@ def svdq_gemm_w4a4_cuda(
         raise ValueError("act, wgt, ascales and wscales are required")
     if not act.is_cuda:
         raise RuntimeError("nunchaku_b200 has no CPU path: act must be a CUDA tensor")
-    if out_vk is not None or out_linearattn is not None:
-        raise NotImplementedError("SANA LiteLA epilogue (out_vk/out_linearattn) is not built yet")
+    litela = out_vk is not None or out_linearattn is not None
+    if litela:
+        # SANA linear attention (launch_impl:311-346): relu(Q) -> out_linearattn, per-head V^T relu(K) state -> out_vk.
+        # The GEMM writes the plain hT projection into a scratch tensor and nb200_litela_vk reduces it while it is L2-hot.
+        if out_vk is None or out_linearattn is None:
+            raise ValueError("out_vk and out_linearattn go together (launch_impl:313)")
+        if out_vk.dtype != torch.float32 or out_vk.dim() != 4 or out_vk.shape[2:] != (33, 32):
+            raise ValueError("out_vk must be float32 [B, heads, 33, 32]")
+        if out_linearattn.dim() != 3 or out_linearattn.shape[0] != out_vk.shape[0]:
+            raise ValueError("out_linearattn must be [B, tokens, N / 3]")
+        if not (out_vk.is_contiguous() and out_linearattn.is_contiguous()):
+            raise ValueError("out_vk / out_linearattn must be contiguous")
+        if out_linearattn.shape[1] % 256 != 0:
+            raise ValueError("tokens must be a multiple of 256 (launch_impl:331)")
+        if out_vk.shape[1] * 96 != wgt.shape[0] or out_linearattn.shape[2] * 3 != wgt.shape[0]:
+            raise ValueError("N must be 3 * heads * 32")
+        out = torch.empty(out_linearattn.shape[0] * out_linearattn.shape[1], wgt.shape[0], dtype=out_linearattn.dtype, device=act.device)
     pack_qkv = out_q is not None or out_k is not None or out_v is not None
     if pack_qkv:
         # EpiloguePackQKV (launch_impl:376-393): fp16 [B=1, heads, rows >= Mp, 128], plain row-major inside a head
@@ -169,6 +184,25 @@ def svdq_gemm_w4a4_cuda(
     args.num_sms = NUM_SMS_OVERRIDE
     args.prof = None if PROF_BUFFER is None else PROF_BUFFER.data_ptr()
     check(lib.nb200_gemm_w4a4(ctypes.byref(args), torch.cuda.current_stream().cuda_stream), "gemm_w4a4")
+    if litela:
+        if out.shape[0] != Mp:
+            raise ValueError("out_linearattn: batch * tokens must equal the padded row count of act")
+        check(lib.nb200_litela_vk(torch_dtype_code(out.dtype), out.data_ptr(), out_linearattn.data_ptr(), out_vk.data_ptr(),
+                                  out_linearattn.shape[0], out_linearattn.shape[1], N, torch.cuda.current_stream().cuda_stream), "litela_vk")
+
+
+def linearattn_vk_mul_q(q: torch.Tensor, vk: torch.Tensor) -> None:
+    """``kernels::linearattn_vk_mul_q`` (src/kernels/zgemm/gemm_w4a4.cu:107-111): in place on ``q`` [B, tokens, heads * 32]
+    (or [B, tokens, heads, 32]) with ``vk`` float32 [B, heads, 33, 32]; eps = 1e-6 as in the reference launcher."""
+    if not (q.is_cuda and vk.is_cuda):
+        raise RuntimeError("nunchaku_b200 has no CPU path")
+    if vk.dtype != torch.float32 or vk.dim() != 4 or vk.shape[2:] != (33, 32) or not vk.is_contiguous():
+        raise ValueError("vk must be contiguous float32 [B, heads, 33, 32]")
+    B, heads = vk.shape[0], vk.shape[1]
+    if not q.is_contiguous() or q.shape[0] != B or q.numel() != B * q.shape[1] * heads * 32:
+        raise ValueError("q must be contiguous [B, tokens, heads * 32]")
+    check(lib.nb200_linearattn_vk_mul_q(torch_dtype_code(q.dtype), q.data_ptr(), vk.data_ptr(), B, q.shape[1], heads, 1e-6,
+                                        torch.cuda.current_stream().cuda_stream), "linearattn_vk_mul_q")
 
 
 _const_cache: dict[tuple, torch.Tensor] = {}

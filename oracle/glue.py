@@ -125,3 +125,32 @@ def split_mod(x: torch.Tensor, n: int) -> list[torch.Tensor]:
 
 def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return _clamp_half(x.to(_F32).to(dtype))
+
+
+# --------------------------------------------------------------------------------------------------
+# SANA linear attention (row a13): EpilogueLiteLA second half + vk_mul_q  (epilogues.cuh:552-760)
+# --------------------------------------------------------------------------------------------------
+def litela_vk(qkv: torch.Tensor):
+    """qkv hT [B, T, N], N = 3 * heads * 32 laid out [Q | per head: K(32) V(32)] ->
+    (relu(Q) hT [B, T, N/3], vk float32 [B, heads, 33, 32]) with fp64 accumulation (the device sums fp32 in an
+    unspecified order)."""
+    B, T, N = qkv.shape
+    heads = N // 96
+    q = torch.clamp_min(qkv[..., : N // 3].to(_F32), 0).to(qkv.dtype)
+    kv = qkv[..., N // 3:].to(torch.float64).view(B, T, heads, 2, 32)
+    k = torch.clamp_min(kv[:, :, :, 0], 0)     # [B, T, H, 32]
+    v = kv[:, :, :, 1]
+    vk = torch.einsum("bthv,bthk->bhvk", v, k)
+    ksum = k.sum(1).unsqueeze(2)                # [B, H, 1, 32]
+    return q, torch.cat([vk, ksum], 2).to(_F32)
+
+
+def vk_mul_q(q: torch.Tensor, vk: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """q hT [B, T, heads*32], vk f32 [B, heads, 33, 32] -> new q.  The device accumulates q[i] * vk[j][i] in fp32 with
+    fused multiply-adds in index order and divides with div.approx; here fp64 dot products and exact division."""
+    B, T, _ = q.shape
+    heads = vk.shape[1]
+    qh = q.view(B, T, heads, 32).to(torch.float64)
+    out = torch.einsum("bthi,bhji->bthj", qh, vk.to(torch.float64))       # [B, T, H, 33]
+    res = out[..., :32] / (out[..., 32:33].to(_F32).to(torch.float64) + np.float32(eps))
+    return res.to(_F32).to(q.dtype).view(B, T, heads * 32)
