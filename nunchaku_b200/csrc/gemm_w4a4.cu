@@ -88,7 +88,10 @@ struct Cfg {
     static constexpr int kBK = FP4 ? 256 : 64;                 // k elements per pipeline stage
     static constexpr int kStages = FP4 ? ((BN == 256 || EPI == EPI_QUANT) ? 3 : 4) : 4;  // TMA ring depth
     static constexpr int kConvStages = 2;                      // INT4: converted-tile ring depth
-    static constexpr int kNumAcc = FP4 ? (BN <= 128 ? 2 : 1) : 2;
+    // INT4 fused-quantise tiles of 256 columns keep ONE accumulator: 256 + the D2 columns must fit TMEM, and an INT4
+    // main loop (~48 k-blocks x ~1000 clk) dwarfs the exposed epilogue
+    static constexpr int kNumAcc = FP4 ? (BN <= 128 ? 2 : 1) : ((EPI == EPI_QUANT && BN == 256) ? 1 : 2);
+    static constexpr int kMaxRdp = BN == 256 ? 32 : nb200::kMaxRdp;   // fused next-layer rank supported by this tile shape
     static constexpr int kABytes = FP4 ? BM * 128 : BM * 32;   // packed A tile per stage
     static constexpr int kBBytes = FP4 ? BN * 128 : BN * 32;
     static constexpr int kSfaCols = 16;                         // 4 K64 blocks x 4 columns
@@ -105,7 +108,7 @@ struct Cfg {
     static constexpr int kThreads = FP4 ? (4 + 4 * kEpiGroups) * 32 : (kConvWarp0 + kConvWarps) * 32;
     static_assert(!FP4 || kTmemSfb + kSfbCols <= 512, "TMEM budget");
     static_assert(kNumAcc * BN <= 512, "TMEM budget");
-    static_assert(EPI != EPI_QUANT || (BN == 128 && kTmemLd + kMaxRdp <= 512), "fused quantise epilogue uses 128-wide tiles");
+    static_assert(EPI != EPI_QUANT || ((BN == 128 || !FP4) && kTmemLd + kMaxRdp <= 512), "fused quantise epilogue: TMEM budget");
     static_assert(EPI != EPI_ROPE || BN == 128, "RMSNorm+RoPE epilogue: one 128-wide head per tile");
 };
 
@@ -127,7 +130,7 @@ struct alignas(1024) Smem {
     // epilogue staging for TMA store: [128 rows][64 cols] hT, 128B swizzle, double buffered
     alignas(1024) uint8_t out_stage[2][BM * 128];
     // EPI_QUANT: next layer's lora_down, per 64-column chunk a K-major 128B-swizzled [Rdp][64] tile
-    alignas(1024) uint8_t ld_b[EPI == EPI_QUANT ? (BN / 64) * kMaxRdp * 128 : 16];
+    alignas(1024) uint8_t ld_b[EPI == EPI_QUANT ? (BN / 64) * C::kMaxRdp * 128 : 16];
     float bias[BN];
     float cscale[BN];
     float ropesum[2][BM];  // EPI_ROPE with two epilogue groups: per-row partial sums of squares
@@ -320,7 +323,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         mbar_expect_tx(&s.ld_b_full, (BN / 64) * p.Rdp * 128);
 #pragma unroll
                         for (int ch = 0; ch < BN / 64; ch++)
-                            tma_load_2d(s.ld_b + ch * kMaxRdp * 128, &tm_ld, &s.ld_b_full, n0 + ch * 64, 0);
+                            tma_load_2d(s.ld_b + ch * C::kMaxRdp * 128, &tm_ld, &s.ld_b_full, n0 + ch * 64, 0);
                         ld_phase ^= 1;
                     }
                 }
@@ -639,7 +642,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                             // D2[128 x Rdp] += G[128 x 64] * Ld_next[Rdp x 64]^T, staged tile doubles as the A operand
                             tc_fence_after_sync();
                             const uint32_t a_addr = smem_u32(s.out_stage[buf]);
-                            const uint32_t b_addr = smem_u32(s.ld_b + ch * kMaxRdp * 128);
+                            const uint32_t b_addr = smem_u32(s.ld_b + ch * C::kMaxRdp * 128);
                             const uint32_t idesc_ld = make_idesc_f16(Tr::kIsBf16, BM, p.Rdp);
 #pragma unroll
                             for (int j = 0; j < 4; j++)
@@ -962,7 +965,15 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
 
 template <bool FP4, typename hT>
 int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
-    if (a.qout != nullptr) return launch<FP4, hT, 128, EPI_QUANT>(a, stream);
+    if (a.qout != nullptr) {
+        // INT4: 256-wide tiles halve the converter work per MMA cycle (the INT4 limiter); needs the next layer's rank to fit
+        // the smaller smem / TMEM budget.  block_n = 128 forces the narrow tile.  (NVFP4: the 256-wide variant does not fit smem.)
+        if constexpr (!FP4) {
+            if (a.block_n != 128 && a.N % 256 == 0 && a.R_down <= 32 && (a.block_n == 256 || (a.Mp / BM) * (a.N / 256) >= 96))
+                return launch<FP4, hT, 256, EPI_QUANT>(a, stream);
+        }
+        return launch<FP4, hT, 128, EPI_QUANT>(a, stream);
+    }
     if (a.rotary_emb != nullptr) return launch<FP4, hT, 128, EPI_ROPE>(a, stream);
     if (a.block_n == 512) {  // CTA pairs (cta_group::2), 256 x 256 tiles
         if (a.N % 256 != 0) return fail(NB200_ERR_INVALID_ARGUMENT, "the CTA-pair kernel needs N % 256 == 0");

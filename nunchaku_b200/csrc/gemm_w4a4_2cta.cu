@@ -46,6 +46,7 @@ struct Gemm2Params {
     int num_n_blocks, num_tiles;   // pair tiles
     int mid_act, act_unsigned;
     long long *prof;  // optional [grid][16] cycle counters (tools/gemm_prof.py)
+    int debug;        // NB200_GEMM_DEBUG ablation bits (see gemm_w4a4.cu): 4 = no main-loop MMAs, 8 = no epilogue math/stores
     float lora_scales[NB200_MAX_LORA_SCALES];
 };
 
@@ -299,7 +300,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                                     make_smem_desc(smem_u32(s.sb[st.idx] + h * 2048 + j * 512), 0, 128, kLayoutNoSwizzle));
                         }
                         const uint32_t a_addr = smem_u32(s.a[st.idx]), b_addr = smem_u32(s.b[st.idx]);
-                        for (int j = 0; j < nj; j++)
+                        for (int j = 0; j < ((p.debug & 4) ? 0 : nj); j++)
                             tc_mma_nvf4_cg2(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
                                             idesc_main, tmem_base + C::kTmemSfa + 4 * j, tmem_base + C::kTmemSfb + 8 * j,
                                             (kb | j) != 0);
@@ -467,8 +468,10 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                 tmem_ld_wait();
                 tc_fence_before_sync();
                 mbar_arrive_cluster(tmem_empty_leader);
-                do_chunk(ch0, va, vb);
-                do_chunk(ch0 + 1, vc, vd);
+                if (!(p.debug & 8)) {
+                    do_chunk(ch0, va, vb);
+                    do_chunk(ch0 + 1, vc, vd);
+                }
             } else {
 #pragma unroll 1
                 for (int cc = 0; cc < CH / H; cc++) {
@@ -481,7 +484,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                         tc_fence_before_sync();
                         mbar_arrive_cluster(tmem_empty_leader);
                     }
-                    do_chunk(ch, v0, v1);
+                    if (!(p.debug & 8)) do_chunk(ch, v0, v1);
                 }
             }
         }
@@ -594,6 +597,8 @@ int launch2(const nb200_gemm_args &a, cudaStream_t stream) {
     p.mid_act = a.mid_act;
     p.act_unsigned = a.act_unsigned;
     p.prof = static_cast<long long *>(a.prof);
+    static const int dbg = getenv("NB200_GEMM_DEBUG") ? atoi(getenv("NB200_GEMM_DEBUG")) : 0;
+    p.debug = dbg;
     for (int i = 0; i < NB200_MAX_LORA_SCALES; i++) p.lora_scales[i] = a.lora_scales[i];
 
     static int num_sms_cached = 0;

@@ -137,7 +137,7 @@ def litela_vk(qkv: torch.Tensor):
     B, T, N = qkv.shape
     heads = N // 96
     q = torch.clamp_min(qkv[..., : N // 3].to(_F32), 0).to(qkv.dtype)
-    kv = qkv[..., N // 3:].to(torch.float64).view(B, T, heads, 2, 32)
+    kv = qkv[..., N // 3:].to(torch.float64).reshape(B, T, heads, 2, 32)
     k = torch.clamp_min(kv[:, :, :, 0], 0)     # [B, T, H, 32]
     v = kv[:, :, :, 1]
     vk = torch.einsum("bthv,bthk->bhvk", v, k)

@@ -103,6 +103,49 @@ def test_fused_gelu_quantize_next(fp4, hT, with_out, R2):
             assert e2 <= 1e-2, diag("lora_act_out", la_out[:M], r_ex.lora_act_out[:M])
 
 
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("R2", [32, 16, 0])
+def test_fused_gelu_quantize_next_int4_wide_tiles(hT, R2):
+    """INT4 fused epilogue on 256-wide tiles (one TMEM accumulator, next-layer rank <= 32), two tiles per m-block so the
+    down projection accumulates in TMEM across tiles before it is flushed: same outputs as the 128-wide kernel."""
+    from nunchaku_b200.ops import gemm as G
+
+    N, K, R, M = 512, 256, 32, 600
+    layer = O.make_synthetic_layer(N, K, R, fp4=False, hT=hT, seed=151)
+    g = torch.Generator().manual_seed(152)
+    nxt_smooth = (torch.rand(N, generator=g) + 0.5).to(hT)
+    nxt_ld = (torch.randn(32, N, generator=g) * 0.05).to(hT)[:R2] if R2 else None
+    x = O.make_activations(M, K, hT, seed=153, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=False)
+    Mp = qa.q.shape[0]
+    params = ref_layout_params(layer)
+    act, asc = _pack_act(qa, False, hT)
+    res = {}
+    for bn in (128, 256):
+        out = torch.full((M, N), float("nan"), dtype=hT, device="cuda")
+        qout = torch.zeros(Mp, N // 2, dtype=torch.uint8, device="cuda")
+        osc = torch.zeros(N // 64, Mp, dtype=hT, device="cuda")
+        la_out = torch.full((Mp, R2), float("nan"), dtype=torch.float32, device="cuda") if R2 else None
+        G.BLOCK_N_OVERRIDE = bn
+        try:
+            G.svdq_gemm_w4a4_cuda(
+                act=act, wgt=params["qweight"], out=out, qout=qout, ascales=asc, wscales=params["wscales"], oscales=osc,
+                lora_act_in=qa.lora_act.cuda(), lora_up=params["proj_up"],
+                lora_down=F.pack_lowrank(nxt_ld, down=True).cuda() if R2 else None, lora_act_out=la_out, bias=params["bias"],
+                smooth_factor=F.pack_channel_vector(nxt_smooth).cuda(), fp4=False)
+        finally:
+            G.BLOCK_N_OVERRIDE = 0
+        torch.cuda.synchronize()
+        res[bn] = (out.cpu(), qout.cpu(), osc.cpu(), None if la_out is None else la_out.cpu())
+    a, b = res[128], res[256]
+    assert torch.equal(a[0].view(torch.int16), b[0].view(torch.int16))     # the hT GELU tile
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2].view(torch.int16), b[2].view(torch.int16))   # codes + scales
+    if R2:
+        assert (a[3][:M] - b[3][:M]).norm() <= 1e-5 * a[3][:M].norm()        # fp32 summation order only
+        ref = (a[0][:M].double() @ nxt_ld.double().t())
+        assert (b[3][:M].double() - ref).norm() <= 1e-4 * ref.norm()
+
+
 @pytest.mark.parametrize("precision", ["int4", "nvfp4"])
 def test_fused_gelu_mlp_module_chain(precision):
     """fused_gelu_mlp(x, fc1, fc2) (ops/fused.py:14-79) end to end vs the oracle chain."""
