@@ -150,7 +150,7 @@ def vk_mul_q(q: torch.Tensor, vk: torch.Tensor, eps: float = 1e-6) -> torch.Tens
     fused multiply-adds in index order and divides with div.approx; here fp64 dot products and exact division."""
     B, T, _ = q.shape
     heads = vk.shape[1]
-    qh = q.view(B, T, heads, 32).to(torch.float64)
+    qh = q.reshape(B, T, heads, 32).to(torch.float64)
     out = torch.einsum("bthi,bhji->bthj", qh, vk.to(torch.float64))       # [B, T, H, 33]
     res = out[..., :32] / (out[..., 32:33].to(_F32).to(torch.float64) + np.float32(eps))
-    return res.to(_F32).to(q.dtype).view(B, T, heads * 32)
+    return res.to(_F32).to(q.dtype).reshape(B, T, heads * 32)
