@@ -98,7 +98,11 @@ struct Cfg {
     static constexpr int kSfbCols = BN / 8;                     // 4 K64 blocks x BN/32 columns
     static constexpr int kTmemSfa = kNumAcc * BN;
     static constexpr int kTmemSfb = kTmemSfa + kSfaCols;
-    static constexpr int kTmemLd = FP4 ? kTmemSfb + kSfbCols : kNumAcc * BN;  // EPI_QUANT: D2 [128 x Rdp]
+    // scale factors are DOUBLE BUFFERED in TMEM (set = k-stage parity): with one set the tcgen05.cp of stage s+1 has a
+    // write-after-read hazard on the columns the MMAs of stage s are reading, so copies and MMAs serialise in the tensor
+    // pipe (measured: ~1000 clk per k-stage with the MMAs removed -- the 12 copies alone -- against 512 clk of MMA)
+    static constexpr int kSfSet = kSfaCols + kSfbCols;
+    static constexpr int kTmemLd = FP4 ? kTmemSfa + 2 * kSfSet : kNumAcc * BN;  // EPI_QUANT: D2 [128 x Rdp]
     // FP4 mainloops are 4x shorter than INT4 ones, so the epilogue is the bottleneck (measured: the fused
     // fc1 epilogue needs ~5k issue cycles per 128x128 tile against a 3k-cycle mainloop): two half-groups of
     // 4 warps drain the two column halves of a tile concurrently.  INT4 keeps one group (its 8 converter
@@ -106,7 +110,7 @@ struct Cfg {
     static constexpr int kEpiGroups = FP4 ? 2 : 1;
     static constexpr int kEpiThreads = 128 * kEpiGroups;
     static constexpr int kThreads = FP4 ? (4 + 4 * kEpiGroups) * 32 : (kConvWarp0 + kConvWarps) * 32;
-    static_assert(!FP4 || kTmemSfb + kSfbCols <= 512, "TMEM budget");
+    static_assert(!FP4 || kTmemSfa + 2 * kSfSet <= 512, "TMEM budget");
     static_assert(kNumAcc * BN <= 512, "TMEM budget");
     static_assert(EPI != EPI_QUANT || ((BN == 128 || !FP4) && kTmemLd + kMaxRdp <= 512), "fused quantise epilogue: TMEM budget");
     static_assert(EPI != EPI_ROPE || BN == 128, "RMSNorm+RoPE epilogue: one 128-wide head per tile");
@@ -352,20 +356,21 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         if (t_first == 0) t_first = clock64() - t_mma0;
                         tc_fence_after_sync();
                         const int nj = min(4, k64_total - 4 * kb);
+                        const uint32_t sf_set = tmem_base + (kb & 1) * C::kSfSet;
                         for (int j = 0; j < nj; j++) {
-                            tc_cp_32x128b_warpx4(tmem_base + C::kTmemSfa + 4 * j,
+                            tc_cp_32x128b_warpx4(sf_set + C::kTmemSfa + 4 * j,
                                                  make_smem_desc(smem_u32(s.sa[st.idx] + j * 512), 0, 128, kLayoutNoSwizzle));
 #pragma unroll
                             for (int h = 0; h < BN / 128; h++)
                                 tc_cp_32x128b_warpx4(
-                                    tmem_base + C::kTmemSfb + (BN / 32) * j + 4 * h,
+                                    sf_set + C::kTmemSfb + (BN / 32) * j + 4 * h,
                                     make_smem_desc(smem_u32(s.sb[st.idx] + h * 2048 + j * 512), 0, 128, kLayoutNoSwizzle));
                         }
                         const uint32_t a_addr = smem_u32(s.a[st.idx]), b_addr = smem_u32(s.b[st.idx]);
                         for (int j = 0; j < ((p.debug & 4) ? 0 : nj); j++)
                             tc_mma_nvf4(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
-                                        idesc_main, tmem_base + C::kTmemSfa + 4 * j,
-                                        tmem_base + C::kTmemSfb + (BN / 32) * j, (kb | j) != 0);
+                                        idesc_main, sf_set + C::kTmemSfa + 4 * j, sf_set + C::kTmemSfb + (BN / 32) * j,
+                                        (kb | j) != 0);
                         tc_commit(&s.empty[st.idx]);
                         st.advance(C::kStages);
                     } else {

@@ -64,7 +64,8 @@ struct Cfg2 {
     static constexpr int kEpiGroups = FP4 ? 2 : 1;   // see gemm_w4a4.cu: FP4 tiles are epilogue bound
     static constexpr int kEpiThreads = 128 * kEpiGroups;
     static constexpr int kThreads = FP4 ? (4 + 4 * kEpiGroups) * 32 : 512;
-    static_assert(!FP4 || kTmemSfb + 32 <= 512, "TMEM budget");
+    static constexpr int kSfSet = 16 + 32;   // SFA + SFB columns of one k-stage; two sets, see gemm_w4a4.cu
+    static_assert(!FP4 || kTmemSfa + 2 * kSfSet <= 512, "TMEM budget");
 };
 
 template <bool FP4>
@@ -290,19 +291,20 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                         if (t_first == 0) t_first = clock64() - t_mma0;
                         tc_fence_after_sync();
                         const int nj = min(4, k64_total - 4 * kb);
+                        const uint32_t sf_set = tmem_base + (kb & 1) * C::kSfSet;
                         for (int j = 0; j < nj; j++) {
-                            tc_cp_32x128b_warpx4_cg2(tmem_base + C::kTmemSfa + 4 * j,
+                            tc_cp_32x128b_warpx4_cg2(sf_set + C::kTmemSfa + 4 * j,
                                                      make_smem_desc(smem_u32(s.sa[st.idx] + j * 512), 0, 128, kLayoutNoSwizzle));
 #pragma unroll
                             for (int h = 0; h < 2; h++)
                                 tc_cp_32x128b_warpx4_cg2(
-                                    tmem_base + C::kTmemSfb + 8 * j + 4 * h,
+                                    sf_set + C::kTmemSfb + 8 * j + 4 * h,
                                     make_smem_desc(smem_u32(s.sb[st.idx] + h * 2048 + j * 512), 0, 128, kLayoutNoSwizzle));
                         }
                         const uint32_t a_addr = smem_u32(s.a[st.idx]), b_addr = smem_u32(s.b[st.idx]);
                         for (int j = 0; j < ((p.debug & 4) ? 0 : nj); j++)
                             tc_mma_nvf4_cg2(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
-                                            idesc_main, tmem_base + C::kTmemSfa + 4 * j, tmem_base + C::kTmemSfb + 8 * j,
+                                            idesc_main, sf_set + C::kTmemSfa + 4 * j, sf_set + C::kTmemSfb + 8 * j,
                                             (kb | j) != 0);
                         tc_commit_cg2(&s.empty[st.idx], 3);
                         st.advance(C::kStages);
