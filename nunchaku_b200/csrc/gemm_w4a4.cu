@@ -85,15 +85,19 @@ constexpr int kMaxRdp = 128;  // largest fused next-layer rank (smem / TMEM budg
 
 template <bool FP4, int BN, int EPI = EPI_DEFAULT>
 struct Cfg {
-    static constexpr int kBK = FP4 ? 256 : 64;                 // k elements per pipeline stage
-    static constexpr int kStages = FP4 ? ((BN == 256 || EPI == EPI_QUANT) ? 3 : 4) : 4;  // TMA ring depth
+    // NVFP4 k-stage = kK64 blocks of 64 elements.  The plain 256-wide tile uses HALF stages (two K64 blocks, 64-byte rows,
+    // SWIZZLE_64B) in a ring twice as deep: the main loop is bound by the TMA round trip (~3000 clk) times the bytes in
+    // flight, and with three 51 KB stages one of them is always the one being consumed
+    static constexpr int kK64 = FP4 ? ((BN == 256 && EPI == EPI_DEFAULT) ? 2 : 4) : 1;
+    static constexpr int kBK = 64 * kK64;                       // k elements per pipeline stage
+    static constexpr int kStages = FP4 ? (kK64 == 2 ? 6 : ((BN == 256 || EPI == EPI_QUANT) ? 3 : 4)) : 4;  // TMA ring depth
     static constexpr int kConvStages = 2;                      // INT4: converted-tile ring depth
     // INT4 fused-quantise tiles of 256 columns keep ONE accumulator: 256 + the D2 columns must fit TMEM, and an INT4
     // main loop (~48 k-blocks x ~1000 clk) dwarfs the exposed epilogue
     static constexpr int kNumAcc = FP4 ? (BN <= 128 ? 2 : 1) : ((EPI == EPI_QUANT && BN == 256) ? 1 : 2);
     static constexpr int kMaxRdp = BN == 256 ? 32 : nb200::kMaxRdp;   // fused next-layer rank supported by this tile shape
-    static constexpr int kABytes = FP4 ? BM * 128 : BM * 32;   // packed A tile per stage
-    static constexpr int kBBytes = FP4 ? BN * 128 : BN * 32;
+    static constexpr int kABytes = BM * 32 * kK64;              // packed A tile per stage (32 bytes per row and K64 block)
+    static constexpr int kBBytes = BN * 32 * kK64;
     static constexpr int kSfaCols = 16;                         // 4 K64 blocks x 4 columns
     static constexpr int kSfbCols = BN / 8;                     // 4 K64 blocks x BN/32 columns
     static constexpr int kTmemSfa = kNumAcc * BN;
@@ -123,8 +127,8 @@ struct alignas(1024) Smem {
     alignas(1024) uint8_t a[C::kStages][C::kABytes];
     alignas(1024) uint8_t b[C::kStages][C::kBBytes];
     // FP4: scale-factor tiles (tcgen05.cp layout).  INT4: per-group scales (hT)
-    alignas(128) uint8_t sa[C::kStages][FP4 ? 4 * 512 : BM * 2];
-    alignas(128) uint8_t sb[C::kStages][FP4 ? (BN / 128) * 4 * 512 : BN * 2];
+    alignas(128) uint8_t sa[C::kStages][FP4 ? C::kK64 * 512 : BM * 2];
+    alignas(128) uint8_t sb[C::kStages][FP4 ? (BN / 128) * C::kK64 * 512 : BN * 2];
     // INT4: converted hT tiles, 128B-swizzled K-major [rows][64]
     alignas(1024) uint8_t a_cv[FP4 ? 1 : C::kConvStages][FP4 ? 16 : BM * 128];
     alignas(1024) uint8_t b_cv[FP4 ? 1 : C::kConvStages][FP4 ? 16 : BN * 128];
@@ -225,7 +229,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k64_total = p.K >> 6;
-    const int num_kblocks = FP4 ? (k64_total + 3) >> 2 : k64_total;
+    const int num_kblocks = (k64_total + C::kK64 - 1) / C::kK64;
     const int lora_chunks = p.lora_up != nullptr ? p.Rp / kLoraChunk : 0;
     // tile schedule: round-robin (tile = cta + i * grid) or, for the fused down projection, one contiguous range per
     // CTA so that consecutive tiles share the m-block and the projection keeps accumulating in TMEM
@@ -287,17 +291,17 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     NB200_TIMED(t_empty, mbar_wait(&s.empty[st.idx], st.phase ^ 1));
                     if constexpr (FP4) {
-                        const int nj = min(4, k64_total - 4 * kb);
+                        const int nj = min(C::kK64, k64_total - C::kK64 * kb);
                         const uint32_t sf_bytes = nj * 512;
                         mbar_expect_tx(&s.full[st.idx], C::kABytes + C::kBBytes + sf_bytes * (1 + BN / 128));
-                        tma_load_2d(s.a[st.idx], &tm_act, &s.full[st.idx], kb * 128, m0);
-                        tma_load_2d(s.b[st.idx], &tm_wgt, &s.full[st.idx], kb * 128, n0);
-                        bulk_load(s.sa[st.idx], p.sfa + (static_cast<size_t>(mb) * k64_total + 4 * kb) * 512, sf_bytes,
+                        tma_load_2d(s.a[st.idx], &tm_act, &s.full[st.idx], kb * 32 * C::kK64, m0);
+                        tma_load_2d(s.b[st.idx], &tm_wgt, &s.full[st.idx], kb * 32 * C::kK64, n0);
+                        bulk_load(s.sa[st.idx], p.sfa + (static_cast<size_t>(mb) * k64_total + C::kK64 * kb) * 512, sf_bytes,
                                   &s.full[st.idx]);
 #pragma unroll
                         for (int h = 0; h < BN / 128; h++)
-                            bulk_load(s.sb[st.idx] + h * 2048,
-                                      p.sfb + (static_cast<size_t>(n0 / 128 + h) * k64_total + 4 * kb) * 512, sf_bytes,
+                            bulk_load(s.sb[st.idx] + h * C::kK64 * 512,
+                                      p.sfb + (static_cast<size_t>(n0 / 128 + h) * k64_total + C::kK64 * kb) * 512, sf_bytes,
                                       &s.full[st.idx]);
                     } else {
                         mbar_expect_tx(&s.full[st.idx], C::kABytes + C::kBBytes + BM * 2 + BN * 2);
@@ -355,8 +359,13 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         NB200_TIMED(t_full, mbar_wait(&s.full[st.idx], st.phase));
                         if (t_first == 0) t_first = clock64() - t_mma0;
                         tc_fence_after_sync();
-                        const int nj = min(4, k64_total - 4 * kb);
+                        const int nj = min(C::kK64, k64_total - C::kK64 * kb);
                         const uint32_t sf_set = tmem_base + (kb & 1) * C::kSfSet;
+                        // operand rows are 32 * kK64 bytes: 128-byte rows -> SWIZZLE_128B atoms of 1024 B, 64-byte rows -> SWIZZLE_64B
+                        // atoms of 512 B; the K64 block j starts 32 * j bytes into the row
+                        auto op_desc = [](uint32_t addr) {
+                            return C::kK64 == 4 ? make_sw128_kmajor_desc(addr) : make_smem_desc(addr, 16, 512, kLayoutSw64);
+                        };
                         for (int j = 0; j < nj; j++) {
                             tc_cp_32x128b_warpx4(sf_set + C::kTmemSfa + 4 * j,
                                                  make_smem_desc(smem_u32(s.sa[st.idx] + j * 512), 0, 128, kLayoutNoSwizzle));
@@ -364,12 +373,11 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                             for (int h = 0; h < BN / 128; h++)
                                 tc_cp_32x128b_warpx4(
                                     sf_set + C::kTmemSfb + (BN / 32) * j + 4 * h,
-                                    make_smem_desc(smem_u32(s.sb[st.idx] + h * 2048 + j * 512), 0, 128, kLayoutNoSwizzle));
+                                    make_smem_desc(smem_u32(s.sb[st.idx] + h * C::kK64 * 512 + j * 512), 0, 128, kLayoutNoSwizzle));
                         }
                         const uint32_t a_addr = smem_u32(s.a[st.idx]), b_addr = smem_u32(s.b[st.idx]);
                         for (int j = 0; j < ((p.debug & 4) ? 0 : nj); j++)
-                            tc_mma_nvf4(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
-                                        idesc_main, sf_set + C::kTmemSfa + 4 * j, sf_set + C::kTmemSfb + (BN / 32) * j,
+                            tc_mma_nvf4(tmem_d, op_desc(a_addr + j * 32), op_desc(b_addr + j * 32), idesc_main, sf_set + C::kTmemSfa + 4 * j, sf_set + C::kTmemSfb + (BN / 32) * j,
                                         (kb | j) != 0);
                         tc_commit(&s.empty[st.idx]);
                         st.advance(C::kStages);
@@ -879,8 +887,9 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     using C = Cfg<FP4, BN, EPI>;
     using S = Smem<FP4, BN, EPI>;
     CUtensorMap tm_act, tm_wgt, tm_out, tm_ld;
-    const CUtensorMapSwizzle in_swz = FP4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
-    const uint32_t in_box = FP4 ? 128 : 32;
+    const CUtensorMapSwizzle in_swz =
+        FP4 ? (C::kK64 == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B) : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const uint32_t in_box = 32 * C::kK64;
     int rc = make_map_2d(&tm_act, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.act, a.K / 2, a.Mp, a.K / 2, in_box, BM, in_swz);
     if (rc) return rc;
     rc = make_map_2d(&tm_wgt, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.wgt, a.K / 2, a.N, a.K / 2, in_box, BN, in_swz);

@@ -336,6 +336,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 constexpr uint32_t kLayoutNoSwizzle = 0;
 constexpr uint32_t kLayoutSw128 = 2;
+constexpr uint32_t kLayoutSw64 = 4;
 
 // K-major operand tile whose rows are exactly 128 bytes, written by TMA with 128B swizzle:
 // 8-row groups are 1024 bytes apart; the leading offset is unused for swizzled K-major tiles.
