@@ -85,10 +85,11 @@ constexpr int kMaxRdp = 128;  // largest fused next-layer rank (smem / TMEM budg
 
 template <bool FP4, int BN, int EPI = EPI_DEFAULT>
 struct Cfg {
-    // NVFP4 k-stage = kK64 blocks of 64 elements.  The plain 256-wide tile uses HALF stages (two K64 blocks, 64-byte rows,
-    // SWIZZLE_64B) in a ring twice as deep: the main loop is bound by the TMA round trip (~3000 clk) times the bytes in
-    // flight, and with three 51 KB stages one of them is always the one being consumed
-    static constexpr int kK64 = FP4 ? ((BN == 256 && EPI == EPI_DEFAULT) ? 2 : 4) : 1;
+    // NVFP4 k-stage = kK64 blocks of 64 elements.  kK64 = 2 (64-byte rows, SWIZZLE_64B, a ring twice as deep) is implemented
+    // and was measured on the plain 256-wide tile: SLOWER (M=4352 K=3072 N=12288: 120.7 vs 100.4 us; load pipeline alone 91 vs
+    // 71 us) -- TMA throughput drops with the row length (32-byte rows ~16, 64-byte ~38, 128-byte ~49 B/clk/SM), so the
+    // full 128-byte rows stay.
+    static constexpr int kK64 = FP4 ? 4 : 1;
     static constexpr int kBK = 64 * kK64;                       // k elements per pipeline stage
     static constexpr int kStages = FP4 ? (kK64 == 2 ? 6 : ((BN == 256 || EPI == EPI_QUANT) ? 3 : 4)) : 4;  // TMA ring depth
     static constexpr int kConvStages = 2;                      // INT4: converted-tile ring depth
