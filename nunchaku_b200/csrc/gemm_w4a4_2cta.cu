@@ -177,7 +177,9 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
     using S = Smem2<FP4>;
     using Tr = HalfTraits<hT>;
     extern __shared__ uint8_t smem_raw[];
-    S &s = *reinterpret_cast<S *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // align inside the SHARED address space (pointer arithmetic on the __shared__ array): a round trip through uintptr_t
+    // makes every access to `s` a generic LD/ST instead of LDS/STS (seen in the ncu source view)
+    S &s = *reinterpret_cast<S *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
     const long long t_kernel0 = clock64();
     const int warp = threadIdx.x >> 5;

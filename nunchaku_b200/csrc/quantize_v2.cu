@@ -92,7 +92,9 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
     using Tr = HalfTraits<hT>;
     using T2 = typename Tr::T2;
     extern __shared__ uint8_t smem_raw[];
-    Q2Smem &s = *reinterpret_cast<Q2Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // align inside the SHARED address space (pointer arithmetic on the __shared__ array): a round trip through uintptr_t
+    // makes every access to `s` a generic LD/ST instead of LDS/STS (seen in the ncu source view)
+    Q2Smem &s = *reinterpret_cast<Q2Smem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
