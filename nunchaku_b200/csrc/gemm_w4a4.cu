@@ -146,10 +146,8 @@ struct alignas(1024) Smem {
     float aux[256];  // EPI_QUANT: next layer's smooth factors of this tile; EPI_ROPE: RMSNorm weights (q | k)
     uint64_t full[C::kStages];
     uint64_t empty[C::kStages];
-    // INT4: each converted stage is handed over in two k-halves (32 k each), converted by two independent groups of 12
-    // warps: four half-stages in flight hide the commit -> cempty -> wake-up latency that a 2-deep ring exposed
-    uint64_t cfull[C::kConvStages][2];
-    uint64_t cempty[C::kConvStages][2];
+    uint64_t cfull[C::kConvStages];
+    uint64_t cempty[C::kConvStages];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint64_t lora_b_full;
@@ -256,10 +254,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             mbar_init(&s.empty[i], FP4 ? 1 : kNumConvThreads / 32);
         }
         for (int i = 0; i < C::kConvStages; i++) {
-            for (int h = 0; h < 2; h++) {
-                mbar_init(&s.cfull[i][h], kNumConvThreads / 64);
-                mbar_init(&s.cempty[i][h], 1);
-            }
+            mbar_init(&s.cfull[i], kNumConvThreads / 32);
+            mbar_init(&s.cempty[i], 1);
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&s.tmem_full[i], 1);
@@ -390,19 +386,16 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         tc_commit(&s.empty[st.idx]);
                         st.advance(C::kStages);
                     } else {
+                        NB200_TIMED(t_full, mbar_wait(&s.cfull[st.idx], st.phase));
+                        if (t_first == 0) t_first = clock64() - t_mma0;
+                        tc_fence_after_sync();
                         const uint32_t a_addr = smem_u32(s.a_cv[st.idx]), b_addr = smem_u32(s.b_cv[st.idx]);
 #pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            NB200_TIMED(t_full, mbar_wait(&s.cfull[st.idx][h], st.phase));
-                            if (t_first == 0) t_first = clock64() - t_mma0;
-                            tc_fence_after_sync();
-#pragma unroll
-                            for (int j = 2 * h; j < 2 * h + 2; j++)
-                                if (!(p.debug & 4))
-                                    tc_mma_f16(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
-                                               idesc_main, (kb | j) != 0);
-                            tc_commit(&s.cempty[st.idx][h]);
-                        }
+                        for (int j = 0; j < 4; j++)
+                            if (!(p.debug & 4))
+                                tc_mma_f16(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32),
+                                           idesc_main, (kb | j) != 0);
+                        tc_commit(&s.cempty[st.idx]);
                         st.advance(C::kConvStages);
                     }
                 }
@@ -845,28 +838,22 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             }
             const uint32_t offA = *reinterpret_cast<uint32_t *>(&offA2);
             const uint32_t offB = *reinterpret_cast<uint32_t *>(&offB2);
-            // two groups of 12 warps (even / odd converter warps, so both sit on all four schedulers): group h converts the
-            // k-half h (32 k = one 16-byte packed unit per row) of every stage: rows 0..127 of A, then the BN rows of B
-            const int cw = ct >> 5;
-            const int grp = cw & 1;
-            const int gt = (cw >> 1) * 32 + lane;   // 0 .. 383 within the group
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     // (no cycle counters here: 768 threads x 4 clock reads per k-block showed up in the ncu source view)
                     mbar_wait(&s.full[pst.idx], pst.phase);
-                    mbar_wait(&s.cempty[cst.idx][grp], cst.phase ^ 1);
+                    mbar_wait(&s.cempty[cst.idx], cst.phase ^ 1);
                     if (!(p.debug & 2)) {
-                        if (gt < BM)
-                            convert_unit<hT>(smem_u32(s.a[pst.idx]), smem_u32(s.a_cv[cst.idx]), gt * 2 + grp, smem_u32(s.sa[pst.idx]), offA,
+                        if (ct < 2 * BM)
+                            convert_unit<hT>(smem_u32(s.a[pst.idx]), smem_u32(s.a_cv[cst.idx]), ct, smem_u32(s.sa[pst.idx]), offA, p.debug & 1);
+                        else if (ct - 2 * BM < 2 * BN)
+                            convert_unit<hT>(smem_u32(s.b[pst.idx]), smem_u32(s.b_cv[cst.idx]), ct - 2 * BM, smem_u32(s.sb[pst.idx]), offB,
                                              p.debug & 1);
-                        else if (gt - BM < BN)
-                            convert_unit<hT>(smem_u32(s.b[pst.idx]), smem_u32(s.b_cv[cst.idx]), (gt - BM) * 2 + grp, smem_u32(s.sb[pst.idx]),
-                                             offB, p.debug & 1);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {  // one arrival per warp
-                        mbar_arrive(&s.cfull[cst.idx][grp]);
+                    if (lane == 0) {  // one arrival per warp: 512 per-thread arrivals per k-block serialise on one word
+                        mbar_arrive(&s.cfull[cst.idx]);
                         mbar_arrive(&s.empty[pst.idx]);
                     }
                     pst.advance(C::kStages);
