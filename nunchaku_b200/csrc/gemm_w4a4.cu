@@ -143,7 +143,8 @@ struct alignas(1024) Smem {
     float bias[BN];
     float cscale[BN];
     float ropesum[2][BM];  // EPI_ROPE with two epilogue groups: per-row partial sums of squares
-    float aux[256];  // EPI_QUANT: next layer's smooth factors of this tile; EPI_ROPE: RMSNorm weights (q | k)
+    float aux[256];  // EPI_QUANT: reciprocals of the next layer's smooth factors of this tile; EPI_ROPE: RMSNorm weights (q | k)
+    float aux2[EPI == EPI_QUANT ? 256 : 1];  // EPI_QUANT: 2^24 pre-scale of denormal smooth factors (1 otherwise)
     uint64_t full[C::kStages];
     uint64_t empty[C::kStages];
     uint64_t cfull[C::kConvStages];
@@ -456,7 +457,14 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             for (int i = eta; i < BN; i += C::kEpiThreads) {
                 s.bias[i] = p.bias != nullptr ? p.bias[n0 + i] : 0.f;
                 s.cscale[i] = p.cscale != nullptr ? p.cscale[n0 + i] : 1.f;
-                if constexpr (EPI == EPI_QUANT) s.aux[i] = Tr::to_float(reinterpret_cast<const hT *>(p.smooth_next)[n0 + i]);
+                if constexpr (EPI == EPI_QUANT) {
+                    // x / smooth is the reference's __fdividef (gemm_w4a4.cuh:930-1043): SASS "if |b| < 2^-126 scale a and b by
+                    // 2^24; MUFU.RCP(b) * a".  Reciprocal and pre-scale depend only on the column: once per tile, not per row.
+                    const float b = Tr::to_float(reinterpret_cast<const hT *>(p.smooth_next)[n0 + i]);
+                    const bool tiny = fabsf(b) < 1.175494350822287508e-38f;
+                    s.aux2[i] = tiny ? 16777216.f : 1.f;
+                    s.aux[i] = rcp_approx(tiny ? b * 16777216.f : b);
+                }
             }
             named_bar_sync(1, C::kEpiThreads);
 
@@ -681,7 +689,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     // ---- next-layer quantisation of (gelu + shift) / smooth  (gemm_w4a4.cuh:930-1043) ---------
                     const int m = m0 + row;
                     uint8_t *qrow = p.qout + static_cast<size_t>(m) * (p.N >> 1) + ((n0 + ch * 64) >> 1);
-                    const float *smo = s.aux + ch * 64;
+                    const float *smo = s.aux + ch * 64;    // rcp.approx of the smooth factors
+                    const float *smk = s.aux2 + ch * 64;   // their denormal pre-scale
                     if constexpr (!FP4) {
                         typename Tr::T2 sh2;
                         sh2.x = Tr::from_float(0.171875f);
@@ -692,7 +701,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                             const typename Tr::T2 gsh = __hadd2(*reinterpret_cast<typename Tr::T2 *>(&gw[i]), sh2);
                             const float2 f = Tr::to_float2(gsh);
                             const typename Tr::T2 d = Tr::from_float2(
-                                make_float2(__fdividef(f.x, smo[2 * i]), __fdividef(f.y, smo[2 * i + 1])));
+                                make_float2((f.x * smk[2 * i]) * smo[2 * i], (f.y * smk[2 * i + 1]) * smo[2 * i + 1]));
                             gw[i] = *reinterpret_cast<const uint32_t *>(&d);
                             const float2 df = Tr::to_float2(d);
                             amax = fmaxf(amax, fmaxf(fabsf(df.x), fabsf(df.y)));
@@ -725,7 +734,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                                 const int wi = g16 * 8 + i;
                                 const float2 f = Tr::to_float2(*reinterpret_cast<typename Tr::T2 *>(&gw[wi]));  // shift is 0 for FP4
                                 const typename Tr::T2 d = Tr::from_float2(
-                                    make_float2(__fdividef(f.x, smo[2 * wi]), __fdividef(f.y, smo[2 * wi + 1])));
+                                    make_float2((f.x * smk[2 * wi]) * smo[2 * wi], (f.y * smk[2 * wi + 1]) * smo[2 * wi + 1]));
                                 gw[wi] = *reinterpret_cast<const uint32_t *>(&d);
                                 const float2 df = Tr::to_float2(d);
                                 amax = fmaxf(amax, fmaxf(fabsf(df.x), fabsf(df.y)));
@@ -888,6 +897,7 @@ template <bool FP4, typename hT, int BN, int EPI>
 int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     using C = Cfg<FP4, BN, EPI>;
     using S = Smem<FP4, BN, EPI>;
+    static_assert(sizeof(S) + 1024 <= 232448, "shared memory budget (227 KB per CTA)");
     CUtensorMap tm_act, tm_wgt, tm_out, tm_ld;
     const CUtensorMapSwizzle in_swz =
         FP4 ? (C::kK64 == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B) : CU_TENSOR_MAP_SWIZZLE_NONE;
