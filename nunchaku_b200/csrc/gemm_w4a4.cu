@@ -446,24 +446,63 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             for (int i = eta; i < 256; i += C::kEpiThreads)
                 s.aux[i] = Tr::to_float(reinterpret_cast<const hT *>(i < 128 ? p.norm_q : p.norm_k)[i & 127]);
         }
+        // Software pipelining of the per-tile global loads (channel vectors, first chunk of the low-rank activations):
+        // they are issued one tile ahead and sit in registers while the current tile's chunks are processed -- two dependent
+        // L2 round trips (~3k clk per tile, a quarter of the fused epilogue) no longer sit on the epilogue's serial path.
+        constexpr int kVecIters = (BN + C::kEpiThreads - 1) / C::kEpiThreads;
+        constexpr bool kPrefetchLora = EPI == EPI_QUANT && FP4;   // register budget: only where the epilogue is the bottleneck
+        float pf_bias[kVecIters], pf_cs[kVecIters];
+        [[maybe_unused]] float pf_sm[kVecIters];
+        [[maybe_unused]] float4 pf_lora[kPrefetchLora ? 2 * (4 / H) : 1];
+        auto prefetch = [&](int t) {
+            if (t >= tile_end) return;
+            const int n0_ = (t % p.num_n_blocks) * BN, m0_ = (t / p.num_n_blocks) * BM;
+#pragma unroll
+            for (int k = 0; k < kVecIters; k++) {
+                const int i = eta + k * C::kEpiThreads;
+                if (i < BN) {
+                    pf_bias[k] = p.bias != nullptr ? p.bias[n0_ + i] : 0.f;
+                    pf_cs[k] = p.cscale != nullptr ? p.cscale[n0_ + i] : 1.f;
+                    if constexpr (EPI == EPI_QUANT) pf_sm[k] = Tr::to_float(reinterpret_cast<const hT *>(p.smooth_next)[n0_ + i]);
+                }
+            }
+            if constexpr (kPrefetchLora) {
+                if (lora_chunks > 0) {
+                    const float *src = p.lora_act + static_cast<size_t>(m0_ + row) * p.R;
+#pragma unroll
+                    for (int oo = 0; oo < 4 / H; oo++) {
+                        const int o = h * (4 / H) + oo;
+                        if (o * 8 < p.R) {
+                            pf_lora[2 * oo] = *reinterpret_cast<const float4 *>(src + o * 8);
+                            pf_lora[2 * oo + 1] = *reinterpret_cast<const float4 *>(src + o * 8 + 4);
+                        }
+                    }
+                }
+            }
+        };
+        prefetch(tile_begin);
         for (int tile = tile_begin; tile < tile_end; tile += tile_step, it++) {
             const int mb = tile / p.num_n_blocks, nb = tile % p.num_n_blocks;
             const int m0 = mb * BM, n0 = nb * BN;
             const int acc = it % C::kNumAcc;
             const long long t_tile0 = clock64();
 
-            // per-tile channel vectors
+            // per-tile channel vectors (prefetched one tile ahead)
             named_bar_sync(1, C::kEpiThreads);
-            for (int i = eta; i < BN; i += C::kEpiThreads) {
-                s.bias[i] = p.bias != nullptr ? p.bias[n0 + i] : 0.f;
-                s.cscale[i] = p.cscale != nullptr ? p.cscale[n0 + i] : 1.f;
-                if constexpr (EPI == EPI_QUANT) {
-                    // x / smooth is the reference's __fdividef (gemm_w4a4.cuh:930-1043): SASS "if |b| < 2^-126 scale a and b by
-                    // 2^24; MUFU.RCP(b) * a".  Reciprocal and pre-scale depend only on the column: once per tile, not per row.
-                    const float b = Tr::to_float(reinterpret_cast<const hT *>(p.smooth_next)[n0 + i]);
-                    const bool tiny = fabsf(b) < 1.175494350822287508e-38f;
-                    s.aux2[i] = tiny ? 16777216.f : 1.f;
-                    s.aux[i] = rcp_approx(tiny ? b * 16777216.f : b);
+#pragma unroll
+            for (int k = 0; k < kVecIters; k++) {
+                const int i = eta + k * C::kEpiThreads;
+                if (i < BN) {
+                    s.bias[i] = pf_bias[k];
+                    s.cscale[i] = pf_cs[k];
+                    if constexpr (EPI == EPI_QUANT) {
+                        // x / smooth is the reference's __fdividef (gemm_w4a4.cuh:930-1043): SASS "if |b| < 2^-126 scale a and b by
+                        // 2^24; MUFU.RCP(b) * a".  Reciprocal and pre-scale depend only on the column: once per tile, not per row.
+                        const float b = pf_sm[k];
+                        const bool tiny = fabsf(b) < 1.175494350822287508e-38f;
+                        s.aux2[i] = tiny ? 16777216.f : 1.f;
+                        s.aux[i] = rcp_approx(tiny ? b * 16777216.f : b);
+                    }
                 }
             }
             named_bar_sync(1, C::kEpiThreads);
@@ -479,8 +518,14 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     const int r0 = c * kLoraChunk + o * 8;
                     uint32_t w[4] = {0, 0, 0, 0};
                     if (r0 < p.R) {
-                        const float4 f0 = *reinterpret_cast<const float4 *>(src + o * 8);
-                        const float4 f1 = *reinterpret_cast<const float4 *>(src + o * 8 + 4);
+                        float4 f0, f1;
+                        if (kPrefetchLora && c == 0) {
+                            f0 = pf_lora[2 * oo];
+                            f1 = pf_lora[2 * oo + 1];
+                        } else {
+                            f0 = *reinterpret_cast<const float4 *>(src + o * 8);
+                            f1 = *reinterpret_cast<const float4 *>(src + o * 8 + 4);
+                        }
                         const float sc = p.lora_scales[r0 >> 4];
                         typename Tr::T2 h0 = Tr::from_float2(make_float2(f0.x * sc, f0.y * sc));
                         typename Tr::T2 h1 = Tr::from_float2(make_float2(f0.z * sc, f0.w * sc));
@@ -497,6 +542,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 mbar_arrive(&s.lora_a_full);
                 lora_phase ^= 1;
             }
+            prefetch(tile + tile_step);   // in flight while this tile's chunks are processed
 
             t_pre += clock64() - t_tile0;
             NB200_TIMED(t_tmem_full, mbar_wait(&s.tmem_full[acc], acc_phase[acc]));
