@@ -4,8 +4,9 @@
 A "step" is one denoising step's worth of the hot path: every SVDQuant linear of the
 FLUX.1-schnell transformer (19 joint blocks x {qkv, out, fc1, fc2} for the 4096-token image
 stream and the 256-token text stream, 38 single blocks x {qkv, out, fc1, fc2} on 4352 tokens)
-= 304 fused W4A4 GEMM launches + 228 activation-quantize launches (fc2's input is quantised inside
-fc1's GEMM epilogue, as in the reference), at the model's exact shapes,
+= 304 fused W4A4 GEMM launches + 228 activation-quantize launches when fc2's input is quantised inside fc1's GEMM
+epilogue as in the reference (INT4, and the 256-token text stream); NVFP4 runs the large-M MLPs as plain GEMM + GELU
+followed by the quantizer (57 more quantize launches, faster on B200 -- DESIGN.md 4.4), at the model's exact shapes,
 rank 32, synthetic random-init 4-bit weights (no checkpoints offline) and synthetic activations.
 Attention / AdaLN / elementwise glue are outside the hot path and not run.
 An image is 4 steps.  value = images/s of this stack, whole job over all ranks.
@@ -167,6 +168,8 @@ class StackRunner:
                 )
             if (M, N) not in self.y:
                 self.y[(M, N)] = torch.empty(M, N, dtype=dtype, device=device)
+        # NVFP4 MLP intermediate [M, 12288] for the large-M path (fc1 plain GEMM + GELU -> quantizer -> fc2)
+        self.hidden = {M: torch.empty(M, MLP, dtype=dtype, device=device) for M in {mm for _, mm, _, _, _, _ in mods} if M >= 2048}
         self.gemm_events = None
         self.launches = 0
 
@@ -205,10 +208,20 @@ class StackRunner:
             if tag.endswith("fc1"):
                 _, _, K2, N2, _, m2 = mods[i + 1]
                 q2, s2, la2 = self.q[(M, K2)]
-                timed(lambda: self.gemm(act=q, wgt=m.qweight, qout=q2, ascales=s, wscales=m.wscales, oscales=s2,
-                                        lora_act_in=la, lora_up=m.proj_up, lora_down=m2.proj_down, lora_act_out=la2,
-                                        bias=m.bias, smooth_factor=m2.smooth_factor, fp4=fp4, alpha=m.wtscale,
-                                        wcscales=m.wcscales), 2 * M * K * N + 2 * M * RANK * N + 2 * M * RANK * N)
+                if fp4 and M >= 2048:
+                    # NVFP4, large M: plain 256-wide GEMM with GELU + the activation quantizer beats the fused 128-wide launch
+                    # (nunchaku_b200.ops.fused._fuse_fc1); one more quantize launch, same arithmetic
+                    hid = self.hidden[M]
+                    timed(lambda: self.gemm(act=q, wgt=m.qweight, out=hid, ascales=s, wscales=m.wscales, lora_act_in=la, lora_up=m.proj_up,
+                                            bias=m.bias, fp4=True, alpha=m.wtscale, wcscales=m.wcscales, fuse_gelu=True),
+                          2 * M * K * N + 2 * M * RANK * N)
+                    self.quant(hid, output=q2, oscales=s2, lora_down=m2.proj_down, lora_act_out=la2, smooth=m2.smooth_factor, fp4=True)
+                    self.launches += 1
+                else:
+                    timed(lambda: self.gemm(act=q, wgt=m.qweight, qout=q2, ascales=s, wscales=m.wscales, oscales=s2,
+                                            lora_act_in=la, lora_up=m.proj_up, lora_down=m2.proj_down, lora_act_out=la2,
+                                            bias=m.bias, smooth_factor=m2.smooth_factor, fp4=fp4, alpha=m.wtscale,
+                                            wcscales=m.wcscales), 2 * M * K * N + 2 * M * RANK * N + 2 * M * RANK * N)
                 timed(lambda: self.gemm(act=q2, wgt=m2.qweight, out=self.y[(M, N2)], ascales=s2, wscales=m2.wscales,
                                         lora_act_in=la2, lora_up=m2.proj_up, bias=m2.bias, fp4=fp4, alpha=m2.wtscale,
                                         wcscales=m2.wcscales, act_unsigned=m2.act_unsigned),

@@ -46,9 +46,13 @@ def svdq_gemm_w4a4_cuda(
     out_k: torch.Tensor | None = None,
     out_v: torch.Tensor | None = None,
     attn_tokens: int = 0,
+    *,
+    fuse_gelu: bool = False,
 ):
     """Fused SVDQuant W4A4 GEMM; positional/keyword compatible with the reference wrapper
     (nunchaku/ops/gemm.py:12-160).  Results are written in place into the provided outputs.
+    ``fuse_gelu`` (keyword-only, not in the reference signature) applies the reference's tanh-GELU in the plain
+    epilogue (C ABI ``mid_act = NB200_ACT_GELU``; the reference only reaches GELU through the fused quantise epilogue).
 
     ``act`` / ``ascales`` / ``lora_act_in`` must come from this package's quantize op (or fused
     epilogue); ``wgt`` / ``wscales`` / ``lora_up`` / ``bias`` / ``wcscales`` are the reference's
@@ -179,7 +183,9 @@ def svdq_gemm_w4a4_cuda(
     args.dtype = torch_dtype_code(dtype)
     args.fp4 = int(fp4)
     args.act_unsigned = int(act_unsigned)
-    args.mid_act = NB200_ACT_SILU if fuse_silu else NB200_ACT_NONE
+    if fuse_silu and fuse_gelu:
+        raise ValueError("fuse_silu and fuse_gelu are exclusive")
+    args.mid_act = NB200_ACT_SILU if fuse_silu else (NB200_ACT_GELU if fuse_gelu else NB200_ACT_NONE)
     args.block_n = BLOCK_N_OVERRIDE
     args.num_sms = NUM_SMS_OVERRIDE
     args.prof = None if PROF_BUFFER is None else PROF_BUFFER.data_ptr()

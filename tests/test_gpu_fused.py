@@ -268,3 +268,35 @@ def test_qkv_pack_outputs(fp4, hT):
         assert (t[:, :, :pad0] == 7.0).all()
     with pytest.raises(ValueError):
         svdq_gemm_w4a4_cuda(out_q=views[0], out_k=views[1], out_v=None, attn_tokens=M, **common)
+
+
+def test_fused_gelu_mlp_nvfp4_both_routes_agree():
+    """NVFP4 MLP: fused fc1 epilogue vs plain GEMM + GELU followed by the activation quantizer (ops.fused.FUSE_FC1_EPILOGUE).
+    Same arithmetic on both routes; only the fp32 summation order of fc2's low-rank hidden state differs."""
+    from nunchaku_b200.models.linear import SVDQW4A4Linear
+    from nunchaku_b200.ops import fused as FU
+
+    hT = torch.bfloat16
+    D, H, R, M = 256, 512, 32, 300
+    l1 = O.make_synthetic_layer(H, D, R, fp4=True, hT=hT, seed=161)
+    l2 = O.make_synthetic_layer(D, H, R, fp4=True, hT=hT, seed=162)
+    x = O.make_activations(M, D, hT, seed=163, smooth=l1.smooth)
+
+    def mk(layer, K, N):
+        p = ref_layout_params(layer)
+        m = SVDQW4A4Linear(K, N, rank=R, bias=True, precision="nvfp4", torch_dtype=hT, device="cuda")
+        m.load_state_dict({"qweight": p["qweight"], "wscales": p["wscales"], "bias": p["bias"], "smooth_factor": p["smooth"],
+                           "smooth_factor_orig": p["smooth"], "proj_down": p["proj_down"], "proj_up": p["proj_up"], "wcscales": p["wcscales"]})
+        m.wtscale = layer.alpha
+        return m
+
+    fc1, fc2 = mk(l1, D, H), mk(l2, H, D)
+    ys = {}
+    for route in (True, False):
+        FU.FUSE_FC1_EPILOGUE = route
+        try:
+            ys[route] = FU.fused_gelu_mlp(x.cuda().view(1, M, D), fc1, fc2).view(M, D).float().cpu()
+        finally:
+            FU.FUSE_FC1_EPILOGUE = None
+    assert (ys[True] - ys[False]).norm() <= 2e-3 * ys[True].norm()
+    assert (ys[True] != ys[False]).float().mean().item() <= 0.05
