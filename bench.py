@@ -5,8 +5,8 @@ A "step" is one denoising step's worth of the hot path: every SVDQuant linear of
 FLUX.1-schnell transformer (19 joint blocks x {qkv, out, fc1, fc2} for the 4096-token image
 stream and the 256-token text stream, 38 single blocks x {qkv, out, fc1, fc2} on 4352 tokens)
 = 304 fused W4A4 GEMM launches + 228 activation-quantize launches when fc2's input is quantised inside fc1's GEMM
-epilogue as in the reference (INT4, and the 256-token text stream); NVFP4 runs the large-M MLPs as plain GEMM + GELU
-followed by the quantizer (57 more quantize launches, faster on B200 -- DESIGN.md 4.4), at the model's exact shapes,
+epilogue as in the reference (the 256-token text stream); the large-M MLPs run as plain GEMM + GELU followed by the
+quantizer (57 more quantize launches, faster on B200 -- DESIGN.md 4.4; NB200_BENCH_SPLIT_MLP=0 fuses them all), at the model's exact shapes,
 rank 32, synthetic random-init 4-bit weights (no checkpoints offline) and synthetic activations.
 Attention / AdaLN / elementwise glue are outside the hot path and not run.
 An image is 4 steps.  value = images/s of this stack, whole job over all ranks.
@@ -170,6 +170,7 @@ class StackRunner:
                 self.y[(M, N)] = torch.empty(M, N, dtype=dtype, device=device)
         # NVFP4 MLP intermediate [M, 12288] for the large-M path (fc1 plain GEMM + GELU -> quantizer -> fc2)
         self.hidden = {M: torch.empty(M, MLP, dtype=dtype, device=device) for M in {mm for _, mm, _, _, _, _ in mods} if M >= 2048}
+        self.split_mlp = os.environ.get("NB200_BENCH_SPLIT_MLP", "1") != "0"
         self.gemm_events = None
         self.launches = 0
 
@@ -208,14 +209,15 @@ class StackRunner:
             if tag.endswith("fc1"):
                 _, _, K2, N2, _, m2 = mods[i + 1]
                 q2, s2, la2 = self.q[(M, K2)]
-                if fp4 and M >= 2048:
-                    # NVFP4, large M: plain 256-wide GEMM with GELU + the activation quantizer beats the fused 128-wide launch
+                if M >= 2048 and self.split_mlp:
+                    # large M: plain 256-wide GEMM with GELU + the activation quantizer beats the fused launch
                     # (nunchaku_b200.ops.fused._fuse_fc1); one more quantize launch, same arithmetic
                     hid = self.hidden[M]
                     timed(lambda: self.gemm(act=q, wgt=m.qweight, out=hid, ascales=s, wscales=m.wscales, lora_act_in=la, lora_up=m.proj_up,
-                                            bias=m.bias, fp4=True, alpha=m.wtscale, wcscales=m.wcscales, fuse_gelu=True),
+                                            bias=m.bias, fp4=fp4, alpha=m.wtscale, wcscales=m.wcscales, fuse_gelu=True),
                           2 * M * K * N + 2 * M * RANK * N)
-                    self.quant(hid, output=q2, oscales=s2, lora_down=m2.proj_down, lora_act_out=la2, smooth=m2.smooth_factor, fp4=True)
+                    self.quant(hid, output=q2, oscales=s2, lora_down=m2.proj_down, lora_act_out=la2, smooth=m2.smooth_factor, fp4=fp4,
+                               shift_unsigned=not fp4)
                     self.launches += 1
                 else:
                     timed(lambda: self.gemm(act=q, wgt=m.qweight, qout=q2, ascales=s, wscales=m.wscales, oscales=s2,

@@ -116,6 +116,11 @@ typedef struct nb200_quantize_args {
      * zero-initialised once; the kernel leaves it clean. */
     void *workspace;
     long long workspace_bytes;
+    /* INT4 only, not in the reference's quantize op: quantise (x + 0.171875) / smooth to UNSIGNED codes (scale = max / 15),
+     * i.e. exactly what the reference's fused GELU epilogue produces for the next layer (EpilogueQuantize<false, true>,
+     * gemm_w4a4_launch_impl.cuh:282-310); the low-rank projection still sees the unshifted input.  Lets a caller split
+     * "GEMM + GELU" and "quantise for fc2" into two launches without changing the numbers.                            */
+    int act_unsigned_shift;
 } nb200_quantize_args;
 
 long long nb200_quantize_workspace_bytes(int Mp, int K);

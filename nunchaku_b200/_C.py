@@ -36,6 +36,7 @@ class QuantizeArgs(ctypes.Structure):
         ("fp4", c_int),
         ("workspace", c_void_p),
         ("workspace_bytes", ctypes.c_longlong),
+        ("act_unsigned_shift", c_int),
     ]
 
 

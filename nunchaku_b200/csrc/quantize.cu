@@ -314,6 +314,7 @@ extern "C" __attribute__((visibility("default"))) int nb200_quantize_w4a4_act_fu
     NB200_REQUIRE(a->dtype == NB200_FP16 || a->dtype == NB200_BF16, "dtype must be fp16 or bf16");
     NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->input) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->output) & 15) == 0,
                   "input/output must be 16-byte aligned");
+    NB200_REQUIRE(!a->act_unsigned_shift || (!a->fp4 && !a->fuse_glu), "act_unsigned_shift is INT4 only and excludes fuse_glu");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!a->fuse_glu) return quantize_v2_dispatch(*a, stream);
     QParams p;

@@ -38,6 +38,7 @@ struct Q2Params {
     float *ws_partial;  // [KS][Mp][32] per rank chunk, or null when KS == 1
     unsigned int *ws_ticket;  // [Mp / 32]
     int M, Mp, K, R, Rp, KS;
+    int unsigned_shift;   // INT4: quantise (x + 0.171875) / smooth to unsigned codes (scale = max / 15)
 };
 
 struct alignas(1024) Q2Smem {
@@ -218,11 +219,24 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                     T2 amax2;          // running |x| max of both halves, NaN-propagating
                     amax2.x = Tr::from_float(0.f);
                     amax2.y = amax2.x;
+                    [[maybe_unused]] T2 vmin2 = amax2;   // unsigned mode: a negative value needs the saturating slow path
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const uint32_t addr = row_addr + ((j ^ (lane & 7)) << 4);
                         const uint4 xv = lds_v4(addr);
                         uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+                        if constexpr (!FP4) {
+                            if (p.unsigned_shift) {   // the fused GELU epilogue's shift, added in hT (launch_impl:286, half2 add)
+                                T2 sh2;
+                                sh2.x = Tr::from_float(0.171875f);
+                                sh2.y = sh2.x;
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const T2 v = __hadd2(*reinterpret_cast<const T2 *>(&xw[e]), sh2);
+                                    xw[e] = *reinterpret_cast<const uint32_t *>(&v);
+                                }
+                            }
+                        }
                         if (smooth != nullptr) {
                             const float4 r0 = *reinterpret_cast<const float4 *>(&s.rsm[warp][j * 8]);
                             const float4 r1 = *reinterpret_cast<const float4 *>(&s.rsm[warp][j * 8 + 4]);
@@ -240,10 +254,15 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                                 const T2 h = Tr::from_float2(a);   // h2div rounds the quotient to hT
                                 xw[e] = *reinterpret_cast<const uint32_t *>(&h);
                             }
-                            sts_v4(addr, xw);
                         }
+                        if (smooth != nullptr || (!FP4 && p.unsigned_shift)) sts_v4(addr, xw);
 #pragma unroll
-                        for (int e = 0; e < 4; e++) amax2 = __hmax2_nan(amax2, __habs2(*reinterpret_cast<const T2 *>(&xw[e])));
+                        for (int e = 0; e < 4; e++) {
+                            amax2 = __hmax2_nan(amax2, __habs2(*reinterpret_cast<const T2 *>(&xw[e])));
+                            if constexpr (!FP4) {
+                                if (p.unsigned_shift) vmin2 = __hmin2(vmin2, *reinterpret_cast<const T2 *>(&xw[e]));
+                            }
+                        }
                     }
                     // phase 2 re-reads the (rounded) row: the 64 values never sit in registers together
                     auto load_chunk = [&](int j, uint32_t (&xw)[4]) {
@@ -258,10 +277,16 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                         const float2 am = Tr::to_float2(amax2);
                         const float amax_p = max_nan(am.x, am.y);
                         uint32_t words[8];
-                        if (amax_p > 0.f && amax_p < 3.0e38f) {
-                            const float s32 = amax_p * (1.0f / 7.0f);
+                        bool regular = amax_p > 0.f && amax_p < 3.0e38f;
+                        if (p.unsigned_shift) {
+                            const float2 mn = Tr::to_float2(vmin2);
+                            regular = regular && fminf(mn.x, mn.y) >= 0.f;
+                        }
+                        if (regular) {
+                            const float s32 = amax_p * (p.unsigned_shift ? (1.0f / 15.0f) : (1.0f / 7.0f));
                             const float rs = rcp_approx_ftz(s32);
                             reinterpret_cast<hT *>(p.scales)[static_cast<size_t>(g) * p.Mp + m] = Tr::from_float(s32);
+                            const float magic = p.unsigned_shift ? 12582912.0f : 12582920.0f;   // unsigned codes are stored as they are
                             // cvt.rni + saturating s4 pack (gemm_utils.cuh:206-246) restated with a magic add: |x * rs| <= 7 + ulp,
                             // so rn(x*rs) + (1.5 * 2^23 + 8) carries round-half-even(x*rs) + 8 in [1, 15] in its low mantissa bits --
                             // the same two roundings (mul, then to integer) as the reference, saturation cannot trigger.
@@ -276,8 +301,8 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
 #pragma unroll
                                 for (int e = 0; e < 4; e++) {
                                     const float2 f = Tr::to_float2(*reinterpret_cast<const T2 *>(&xw[e]));
-                                    const float f0 = __fadd_rn(__fmul_rn(f.x, rs), 12582920.0f);
-                                    const float f1 = __fadd_rn(__fmul_rn(f.y, rs), 12582920.0f);
+                                    const float f0 = __fadd_rn(__fmul_rn(f.x, rs), magic);
+                                    const float f1 = __fadd_rn(__fmul_rn(f.y, rs), magic);
                                     word += (__float_as_uint(f0) << (4 * e)) + (__float_as_uint(f1) << (4 * e + 16));
                                 }
                                 words[j] = word - kBias;
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                                     amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
                                 }
                             }
-                            const float s32 = amax * (1.0f / 7.0f);
+                            const float s32 = amax * (p.unsigned_shift ? (1.0f / 15.0f) : (1.0f / 7.0f));
                             const float rs = rcp_approx_ftz(s32);
                             reinterpret_cast<hT *>(p.scales)[static_cast<size_t>(g) * p.Mp + m] = Tr::from_float(s32);
 #pragma unroll 1
@@ -309,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                                     qv[2 * e] = cvt_rni(f.x * rs);
                                     qv[2 * e + 1] = cvt_rni(f.y * rs);
                                 }
-                                words[j] = pack8_int4_b200<false>(qv);
+                                words[j] = p.unsigned_shift ? pack8_int4_b200<true>(qv) : pack8_int4_b200<false>(qv);
                             }
                         }
                         *reinterpret_cast<uint4 *>(qdst) = make_uint4(words[0], words[1], words[2], words[3]);
@@ -357,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                         *reinterpret_cast<uint32_t *>(sf) = sfw;
                     }
                 }
-                if (chunk == 0 && smooth != nullptr) fence_proxy_async_smem();   // our in-place writes vs the TMA refill of this stage
+                if (chunk == 0 && (smooth != nullptr || (!FP4 && p.unsigned_shift))) fence_proxy_async_smem();   // our in-place writes vs the TMA refill of this stage
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.empty[st]);
             }
@@ -441,6 +466,7 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
     p.K = a.K;
     p.R = a.R;
     p.Rp = (a.R + 31) / 32 * 32;
+    p.unsigned_shift = a.act_unsigned_shift;
     // split K across CTAs only when the row blocks alone would leave most SMs idle
     const int row_blocks = a.Mp / kRows;
     const int G = a.K / 64;

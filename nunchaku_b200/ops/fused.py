@@ -5,6 +5,7 @@ import torch
 
 from ..utils import ceil_divide
 from .gemm import svdq_gemm_w4a4_cuda
+from .quantize import svdq_quantize_w4a4_act_fuse_lora_cuda
 
 
 # NVFP4, large M: where the intermediate goes.  None = choose by shape, True / False = force.  Measured on B200
@@ -12,14 +13,15 @@ from .gemm import svdq_gemm_w4a4_cuda
 # per FLOP is 1/3 higher than the plain 256-wide kernel's; above ~2k rows "plain GEMM with GELU (256-wide) + the
 # activation quantizer" is faster than the fused launch even though the [M, hidden] tensor makes a round trip through
 # L2 / HBM.  Same arithmetic either way (GELU on the hT-rounded value, x / smooth, e2m1 codes + ue4m3 scales, LoRA-down
-# on the unshifted GELU output).  INT4 always fuses: only the epilogue produces the shifted UNSIGNED codes fc2 expects.
+# on the unshifted GELU output).  INT4 takes the same two-launch route through the quantizer's ``shift_unsigned`` mode, which
+# reproduces the epilogue's shifted UNSIGNED codes (fc2 is built with act_unsigned=True either way).
 FUSE_FC1_EPILOGUE: bool | None = None
 
 
 def _fuse_fc1(fc1, rows: int) -> bool:
     if FUSE_FC1_EPILOGUE is not None:
-        return bool(FUSE_FC1_EPILOGUE) or fc1.precision != "nvfp4"
-    return not (fc1.precision == "nvfp4" and rows >= 2048 and fc1.out_features % 256 == 0)
+        return bool(FUSE_FC1_EPILOGUE)
+    return not (rows >= 2048 and fc1.out_features % 256 == 0)
 
 
 def fused_gelu_mlp(x: torch.Tensor, fc1, fc2, pad_size: int = 256) -> torch.Tensor:
@@ -32,9 +34,11 @@ def fused_gelu_mlp(x: torch.Tensor, fc1, fc2, pad_size: int = 256) -> torch.Tens
     quantized_x, ascales, lora_act = fc1.quantize(x)
     if not _fuse_fc1(fc1, batch_size * seq_len):
         hidden = torch.empty(batch_size * seq_len, fc1.out_features, dtype=x.dtype, device=x.device)
+        fp4 = fc1.precision == "nvfp4"
         svdq_gemm_w4a4_cuda(act=quantized_x, wgt=fc1.qweight, out=hidden, ascales=ascales, wscales=fc1.wscales, lora_act_in=lora_act,
-                            lora_up=fc1.proj_up, bias=fc1.bias, fp4=True, alpha=fc1.wtscale, wcscales=fc1.wcscales, fuse_gelu=True)
-        q2, s2, la2 = fc2.quantize(hidden)
+                            lora_up=fc1.proj_up, bias=fc1.bias, fp4=fp4, alpha=fc1.wtscale, wcscales=fc1.wcscales, fuse_gelu=True)
+        q2, s2, la2 = svdq_quantize_w4a4_act_fuse_lora_cuda(hidden, lora_down=fc2.proj_down, smooth=fc2.smooth_factor, fp4=fp4,
+                                                            pad_size=pad_size, shift_unsigned=not fp4)
         output = torch.empty(batch_size * seq_len, fc2.out_features, dtype=x.dtype, device=x.device)
         return fc2.forward_quant(q2, s2, la2, output=output).view(batch_size, seq_len, -1)
     batch_size_pad = ceil_divide(batch_size * seq_len, pad_size) * pad_size

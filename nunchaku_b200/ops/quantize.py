@@ -20,8 +20,14 @@ def svdq_quantize_w4a4_act_fuse_lora_cuda(
     fuse_glu: bool = False,
     fp4: bool = False,
     pad_size: int = 256,
+    *,
+    shift_unsigned: bool = False,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Quantize activations to 4 bit and compute the low-rank down projection.
+
+    ``shift_unsigned`` (keyword-only, INT4, not in the reference signature): quantise ``(x + 0.171875) / smooth`` to unsigned
+    codes with scale = max / 15 -- what the reference's fused GELU epilogue produces for fc2 (launch_impl:282-310) -- while
+    the low-rank projection still sees ``x``; the consumer GEMM must be called with ``act_unsigned=True``.
 
     Same arguments, shapes, dtypes and return value as the reference wrapper
     (nunchaku/ops/quantize.py:10-80).  ``lora_down`` and ``smooth`` arrive in the reference's
@@ -71,6 +77,9 @@ def svdq_quantize_w4a4_act_fuse_lora_cuda(
     args.M, args.Mp, args.K, args.R = batch_size, batch_size_pad, channels, rank
     args.dtype = torch_dtype_code(input.dtype)
     args.fuse_glu, args.fp4 = int(fuse_glu), int(fp4)
+    if shift_unsigned and (fp4 or fuse_glu):
+        raise ValueError("shift_unsigned is INT4 only and excludes fuse_glu")
+    args.act_unsigned_shift = int(shift_unsigned)
     ws = _workspace(batch_size_pad, channels, input.device)
     args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
     check(lib.nb200_quantize_w4a4_act_fuse_lora(ctypes.byref(args), torch.cuda.current_stream().cuda_stream),

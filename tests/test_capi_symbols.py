@@ -47,5 +47,5 @@ def test_struct_layout_matches_header_sizes():
 
     from nunchaku_b200._C import GemmArgs, QuantizeArgs
 
-    assert ctypes.sizeof(QuantizeArgs) == 96
+    assert ctypes.sizeof(QuantizeArgs) == 104
     assert ctypes.sizeof(GemmArgs) == 512

@@ -270,33 +270,61 @@ def test_qkv_pack_outputs(fp4, hT):
         svdq_gemm_w4a4_cuda(out_q=views[0], out_k=views[1], out_v=None, attn_tokens=M, **common)
 
 
-def test_fused_gelu_mlp_nvfp4_both_routes_agree():
-    """NVFP4 MLP: fused fc1 epilogue vs plain GEMM + GELU followed by the activation quantizer (ops.fused.FUSE_FC1_EPILOGUE).
-    Same arithmetic on both routes; only the fp32 summation order of fc2's low-rank hidden state differs."""
+@pytest.mark.parametrize("precision", ["nvfp4", "int4"])
+def test_fused_gelu_mlp_both_routes_agree(precision):
+    """MLP: fused fc1 epilogue vs plain GEMM + GELU followed by the activation quantizer (ops.fused.FUSE_FC1_EPILOGUE; INT4 uses
+    the quantizer's shift_unsigned mode).  Same arithmetic on both routes: the 4-bit codes and scales handed to fc2 must be
+    bit-identical; only the fp32 summation order of fc2's low-rank hidden state differs."""
     from nunchaku_b200.models.linear import SVDQW4A4Linear
     from nunchaku_b200.ops import fused as FU
+    from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
+    from nunchaku_b200.ops.quantize import svdq_quantize_w4a4_act_fuse_lora_cuda
 
+    fp4 = precision == "nvfp4"
     hT = torch.bfloat16
     D, H, R, M = 256, 512, 32, 300
-    l1 = O.make_synthetic_layer(H, D, R, fp4=True, hT=hT, seed=161)
-    l2 = O.make_synthetic_layer(D, H, R, fp4=True, hT=hT, seed=162)
+    l1 = O.make_synthetic_layer(H, D, R, fp4=fp4, hT=hT, seed=161)
+    l2 = O.make_synthetic_layer(D, H, R, fp4=fp4, hT=hT, seed=162)
     x = O.make_activations(M, D, hT, seed=163, smooth=l1.smooth)
 
-    def mk(layer, K, N):
+    def mk(layer, K, N, unsigned):
         p = ref_layout_params(layer)
-        m = SVDQW4A4Linear(K, N, rank=R, bias=True, precision="nvfp4", torch_dtype=hT, device="cuda")
-        m.load_state_dict({"qweight": p["qweight"], "wscales": p["wscales"], "bias": p["bias"], "smooth_factor": p["smooth"],
-                           "smooth_factor_orig": p["smooth"], "proj_down": p["proj_down"], "proj_up": p["proj_up"], "wcscales": p["wcscales"]})
-        m.wtscale = layer.alpha
+        m = SVDQW4A4Linear(K, N, rank=R, bias=True, precision=precision, act_unsigned=unsigned, torch_dtype=hT, device="cuda")
+        sd = {"qweight": p["qweight"], "wscales": p["wscales"], "bias": p["bias"], "smooth_factor": p["smooth"],
+              "smooth_factor_orig": p["smooth"], "proj_down": p["proj_down"], "proj_up": p["proj_up"]}
+        if fp4:
+            sd["wcscales"] = p["wcscales"]
+            m.wtscale = layer.alpha
+        m.load_state_dict(sd)
         return m
 
-    fc1, fc2 = mk(l1, D, H), mk(l2, H, D)
+    fc1, fc2 = mk(l1, D, H, False), mk(l2, H, D, not fp4)
+    xd = x.cuda()
+    # the hand-off tensors of both routes
+    qx, asc, la = fc1.quantize(xd)
+    Mp = qx.shape[0]
+    q_f = torch.zeros(Mp, H // 2, dtype=torch.uint8, device="cuda")
+    s_f = torch.zeros(H // 16, Mp, dtype=torch.float8_e4m3fn, device="cuda") if fp4 else torch.zeros(H // 64, Mp, dtype=hT, device="cuda")
+    la_f = torch.zeros(Mp, R, dtype=torch.float32, device="cuda")
+    common = dict(act=qx, wgt=fc1.qweight, ascales=asc, wscales=fc1.wscales, lora_act_in=la, lora_up=fc1.proj_up, bias=fc1.bias, fp4=fp4,
+                  alpha=fc1.wtscale, wcscales=fc1.wcscales)
+    svdq_gemm_w4a4_cuda(qout=q_f, oscales=s_f, lora_down=fc2.proj_down, lora_act_out=la_f, smooth_factor=fc2.smooth_factor, **common)
+    hid = torch.empty(M, H, dtype=hT, device="cuda")
+    svdq_gemm_w4a4_cuda(out=hid, fuse_gelu=True, **common)
+    q_s, s_s, la_s = svdq_quantize_w4a4_act_fuse_lora_cuda(hid, lora_down=fc2.proj_down, smooth=fc2.smooth_factor, fp4=fp4, shift_unsigned=not fp4)
+    torch.cuda.synchronize()
+    assert torch.equal(q_f[:M].cpu(), q_s[:M].cpu()), "4-bit codes handed to fc2 differ between the routes"
+    if fp4:
+        # scale tiles: only the rows < M are defined
+        assert torch.equal(L.unpack_sf_tiles(s_f.view(torch.uint8).cpu().reshape(-1), Mp, H // 16)[:M], L.unpack_sf_tiles(s_s.view(torch.uint8).cpu().reshape(-1), Mp, H // 16)[:M])
+    else:
+        assert torch.equal(s_f[:, :M].cpu().view(torch.int16), s_s[:, :M].cpu().view(torch.int16))
+    assert (la_f[:M] - la_s[:M]).norm() <= 1e-4 * la_s[:M].norm()
     ys = {}
     for route in (True, False):
         FU.FUSE_FC1_EPILOGUE = route
         try:
-            ys[route] = FU.fused_gelu_mlp(x.cuda().view(1, M, D), fc1, fc2).view(M, D).float().cpu()
+            ys[route] = FU.fused_gelu_mlp(xd.view(1, M, D), fc1, fc2).view(M, D).float().cpu()
         finally:
             FU.FUSE_FC1_EPILOGUE = None
     assert (ys[True] - ys[False]).norm() <= 2e-3 * ys[True].norm()
-    assert (ys[True] != ys[False]).float().mean().item() <= 0.05
