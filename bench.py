@@ -427,7 +427,11 @@ def main() -> int:
             up_free[b].record(cur)
             if i + 1 < n:
                 upload(b ^ 1)
-            y = runner.step()
+            if graph is not None:   # the same per-layer op calls, captured once (outputs are preallocated: the ops are graph-safe)
+                graph.replay()
+                y = runner.y[(IMG_TOKENS + TXT_TOKENS, DIM)]
+            else:
+                y = runner.step()
             cur.wait_event(dn_done[b])                                           # st_out[b] was downloaded two steps ago
             st_out[b].copy_(y, non_blocking=True)
             dn_ready[b].record(cur)
@@ -517,7 +521,8 @@ def main() -> int:
             "timing": timing_mode,
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_images, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "SVDQW4A4 ops (quantize + gemm) launched from Python per layer; pinned host in/out every step, copies on a second stream (double-buffered staging)"},
+                    "path": ("CUDA graph of the per-layer SVDQW4A4 op calls (quantize + gemm)" if timing_mode.startswith("cuda graph") else "SVDQW4A4 ops launched from Python per layer")
+                            + "; pinned host in/out every step, copies on a second stream (double-buffered staging)"},
             "gpu_launches": args.steps * launches_per_step,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -4,11 +4,12 @@
 set -x
 mkdir -p gpurun_out
 TAG=${1:-r01i}
+LAUNCHES=${2:-589}   # kernels per bench step: 304 GEMM + 228 quantize + 57 more quantizes of the split large-M MLPs
 nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/ubench/alu_rates.cu -o gpurun_out/alu_rates && ./gpurun_out/alu_rates | tee gpurun_out/alu_rates_${TAG}.txt
 rm -f gpurun_out/alu_rates
 K='regex:gemm_w4a4|quantize'
 for P in int4 nvfp4; do
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 1596 -c 532 --csv --log-file gpurun_out/launches_${TAG}_$P.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s $((3 * LAUNCHES)) -c $LAUNCHES --csv --log-file gpurun_out/launches_${TAG}_$P.csv \
       python bench.py --steps 1 --warmup 3 --precision $P --no-graph --skip-cpu > gpurun_out/ncu_b_$P.log 2>&1
   tail -2 gpurun_out/ncu_b_$P.log
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_w4a4 -s 3 -c 1 -o gpurun_out/prof_${TAG}_gemm_${P} -f \
