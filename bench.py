@@ -489,11 +489,11 @@ def main() -> int:
     mult = 4.0 if args.precision == "nvfp4" else 1.0
     achieved = g_fl / (g_ms * 1e-3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch on the primary shape (M=4096, K=N=3072, r=32), from the
-    # committed `ncu --set full` captures profiles/r01r_gemm_{int4,nvfp4}_ncu.txt (the 25 MB output stays in L2)
+    # committed `ncu --set full` captures profiles/r01x_gemm_{int4,nvfp4}_ncu.txt (the 25 MB output stays in L2)
     traffic = {"int4": 12.5e6, "nvfp4": 13.2e6}[args.precision]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak * mult, "unit": "TFLOP/s",
                 "frac": achieved / (bf16_peak * mult), "traffic": traffic,
-                "traffic_basis": "bytes per launch, primary shape 4096x3072x3072, ncu r01r (algorithmic: 37.6 MB incl. the 25 MB output that stays in L2)",
+                "traffic_basis": "bytes per launch, primary shape 4096x3072x3072, ncu r01x (algorithmic: 37.6 MB incl. the 25 MB output that stays in L2)",
                 "kernel": "gemm_w4a4_kernel", "launches": len(runner.gemm_events),
                 "avg_launch_us": g_ms * 1e3 / len(runner.gemm_events),
                 "peak_basis": peak_src + (" x4 (FP4 pipe = 4x the 16-bit pipe)" if mult == 4.0 else " (INT4 runs on the 16-bit pipe: tcgen05 has no INT4 kind)")}
