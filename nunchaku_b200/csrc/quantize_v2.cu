@@ -38,6 +38,7 @@ struct Q2Params {
     float *ws_partial;  // [KS][Mp][32] per rank chunk, or null when KS == 1
     unsigned int *ws_ticket;  // [Mp / 32]
     int M, Mp, K, R, Rp, KS;
+    int debug;            // NB200_QUANT_DEBUG ablation bits (results invalid): 1 = skip the low-rank MMAs, 2 = skip the quantise phases
     int unsigned_shift;   // INT4: quantise (x + 0.171875) / smooth to unsigned codes (scale = max / 15)
 };
 
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
 
                 // ---- x @ lora_down^T on the un-smoothed tile (lora.cuh:243-353) ---------------------
 #pragma unroll
-                for (int kb = 0; kb < 2; kb++) {
+                for (int kb = 0; kb < ((p.debug & 1) ? 0 : 2); kb++) {
 #pragma unroll
                     for (int m = 0; m < 2; m++) {
 #pragma unroll
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                 // ---- smooth + quantise: 8 lanes per row, 4 rows per pass (gemm_w4a4.cuh:85-187,429-523) --
                 // ---- smooth + quantise: ONE LANE PER ROW, the whole 64-wide group in registers -- no shuffles,
                 //      8 independent 16-byte chunks of ILP (gemm_w4a4.cuh:85-187,429-523) -----------------------
-                if (chunk == 0) {
+                if (chunk == 0 && !(p.debug & 2)) {
                     const int m = row0 + lane;
                     const uint32_t row_addr = tile + lane * 128;
                     // phase 1: smoothing division (rounded to hT, written back over the lane's own row of the tile) + absmax
@@ -467,6 +468,8 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
     p.R = a.R;
     p.Rp = (a.R + 31) / 32 * 32;
     p.unsigned_shift = a.act_unsigned_shift;
+    static const int dbg = getenv("NB200_QUANT_DEBUG") ? atoi(getenv("NB200_QUANT_DEBUG")) : 0;
+    p.debug = dbg;
     // split K across CTAs only when the row blocks alone would leave most SMs idle
     const int row_blocks = a.Mp / kRows;
     const int G = a.K / 64;
