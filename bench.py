@@ -531,7 +531,7 @@ def main() -> int:
     line = None
     if rank == 0:
         cpu = None
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:   # the CPU baseline is an N=1 figure (rank 0's host cores)
             torch.set_num_threads(min(os.cpu_count() or 1, 32))
             dt, fl = cpu_sample(torch, args.precision, reps=3)
             cpu_v = (fl / dt) / ((f_main + f_lr) * STEPS_PER_IMAGE)
