@@ -316,7 +316,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference has no CPU implementation of this path (SURVEY F6); this is the CPU oracle (port); value extrapolates the sample's FLOP rate to one image's hot-path FLOPs",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -329,7 +329,32 @@ def workload_config(args):
             "l2": "inputs larger than L2 (4.3 GB of 4-bit weights streamed per step)"}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    """stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints "NCCL version ..." on
+    stdout when NCCL_DEBUG is set in the environment).  Point fd 1 at stderr for the run and keep the real stdout for
+    the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main() -> int:
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -553,7 +578,7 @@ def main() -> int:
             "cpu_baseline": cpu,
             "secondary": secondary,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     replica.shutdown()
     return 0
 
