@@ -3,7 +3,11 @@
 import os
 import re
 
+import pytest
+
 from nunchaku_b200._C import SYMBOLS, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 HDR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "nunchaku_b200.h")
 
@@ -49,3 +53,53 @@ def test_struct_layout_matches_header_sizes():
 
     assert ctypes.sizeof(QuantizeArgs) == 104
     assert ctypes.sizeof(GemmArgs) == 512
+
+
+def test_struct_layout_matches_a_c_compiler(tmp_path):
+    """Compile the header with gcc and compare sizeof / offsetof of every struct field with the ctypes mirrors."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from nunchaku_b200._C import GemmArgs, QuantizeArgs
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    fields = {"nb200_quantize_args": QuantizeArgs, "nb200_gemm_args": GemmArgs}
+    prog = ['#include "nunchaku_b200.h"', "#include <stdio.h>", "#include <stddef.h>", "int main(void) {"]
+    for sname, cls in fields.items():
+        prog.append(f'  printf("{sname} %zu\\n", sizeof({sname}));')
+        for fname, _ in cls._fields_:
+            prog.append(f'  printf("{sname}.{fname} %zu\\n", offsetof({sname}, {fname}));')
+    prog += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for sname, cls in fields.items():
+        assert int(out[sname]) == ctypes.sizeof(cls), sname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{sname}.{fname}"]) == getattr(cls, fname).offset, f"{sname}.{fname}"
+
+
+def test_glue_and_litela_entry_points_validate_arguments_without_a_gpu():
+    """Precondition failures are reported before any CUDA call: status -1 and a message, no crash."""
+    from nunchaku_b200._C import lib
+
+    assert lib.nb200_add(1, None, None, None, 16, None) == -1
+    assert b"null" in lib.nb200_last_error().lower()
+    assert lib.nb200_activation(0, 1, 16, 16, 8, None) == -1            # kind must be SILU / GELU
+    assert lib.nb200_activation(1, 7, 16, 16, 8, None) == -1            # unknown dtype
+    assert lib.nb200_layernorm(1, 16, None, None, 16, 4, 12, 1e-6, None) == -1   # hidden % 8 != 0
+    assert lib.nb200_rms_norm(1, 16, None, 16, 4, 64, 1e-6, None) == -1        # weight required
+    assert lib.nb200_mul_add_batch(1, 16, None, 16, 0.0, 1, 12, 1, 12, 0, 0, 0, None) == -1   # sizes % 8
+    assert lib.nb200_cast(1, 16, 1, 16, -1, None) == -1
+    assert lib.nb200_litela_vk(1, 16, 16, 16, 1, 256, 100, None) == -1   # N must be 3 * heads * 32
+    assert lib.nb200_linearattn_vk_mul_q(2, 16, 16, 1, 256, 4, 1e-6, None) == -1   # fp32 q is not supported
+    import ctypes
+
+    arr = (ctypes.c_void_p * 7)(*([16] * 7))
+    assert lib.nb200_split_mod(1, 16, arr, 7, 70, None) == -1            # 2..6 outputs
+    assert lib.nb200_add(1, 16, 16, 16, 0, None) == 0                     # empty tensors are a no-op

@@ -44,3 +44,32 @@ def test_mul_add_is_single_rounding_and_split_roundtrip():
     parts = O.split_mod(x, 4)
     assert torch.equal(torch.stack(parts, -1).reshape(x.shape), x)
     assert O.cast(torch.tensor([1e6, -1e6]), torch.float16).tolist() == [65504.0, -65504.0]
+
+
+def test_litela_oracle_against_naive_loops():
+    """oracle.glue.litela_vk / vk_mul_q vs the definition written as plain loops (epilogues.cuh:552-760)."""
+    g = torch.Generator().manual_seed(3)
+    B, T, heads = 2, 5, 2
+    N = 3 * heads * 32
+    qkv = torch.randn(B, T, N, generator=g).to(torch.bfloat16)
+    q, vk = O.litela_vk(qkv)
+    assert torch.equal(q, torch.clamp_min(qkv[..., : N // 3].float(), 0).to(torch.bfloat16))
+    ref = torch.zeros(B, heads, 33, 32, dtype=torch.float64)
+    for b in range(B):
+        for h in range(heads):
+            for t in range(T):
+                k = torch.clamp_min(qkv[b, t, N // 3 + h * 64: N // 3 + h * 64 + 32].double(), 0)
+                v = qkv[b, t, N // 3 + h * 64 + 32: N // 3 + h * 64 + 64].double()
+                ref[b, h, :32] += v[:, None] * k[None, :]
+                ref[b, h, 32] += k
+    assert torch.allclose(vk.double(), ref, rtol=1e-6, atol=1e-6)
+    out = O.vk_mul_q(q, vk)
+    for b in range(B):
+        for t in range(T):
+            for h in range(heads):
+                qv = q[b, t, h * 32:(h + 1) * 32].double()
+                num = vk[b, h, :32].double() @ qv
+                den = vk[b, h, 32].double() @ qv + 1e-6
+                want = (num / den).float().to(torch.bfloat16)
+                got = out[b, t, h * 32:(h + 1) * 32]
+                assert (got.float() - want.float()).abs().max() <= 2.0 ** -7 * max(1.0, want.float().abs().max().item())
