@@ -1,0 +1,78 @@
+"""CPU: host-side contract of the operator mirror -- what is rejected, and how (no GPU needed).
+
+The reference aborts on precondition failures (`assert` with -UNDEBUG); the mirror raises instead, and it
+never falls back to a CPU computation: CPU tensors are an error, not a slow path."""
+import pytest
+import torch
+
+from nunchaku_b200.models.linear import SVDQW4A4Linear
+from nunchaku_b200.ops import glue
+from nunchaku_b200.ops.fused import _fuse_fc1
+from nunchaku_b200.ops.gemm import linearattn_vk_mul_q, svdq_gemm_w4a4_cuda
+from nunchaku_b200.ops.quantize import svdq_quantize_w4a4_act_fuse_lora_cuda
+from nunchaku_b200.utils import ceil_divide, get_precision, torch_dtype_code
+
+
+def test_gemm_rejects_missing_and_cpu_operands():
+    with pytest.raises(ValueError):
+        svdq_gemm_w4a4_cuda(act=None, wgt=None, ascales=None, wscales=None)
+    act = torch.zeros(256, 64, dtype=torch.uint8)
+    wgt = torch.zeros(128, 64, dtype=torch.int8)
+    sc = torch.zeros(2, 256, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        svdq_gemm_w4a4_cuda(act=act, wgt=wgt, out=torch.zeros(256, 128, dtype=torch.bfloat16), ascales=sc, wscales=sc)
+
+
+def test_quantize_rejects_bad_inputs():
+    x = torch.zeros(4, 128, dtype=torch.bfloat16)
+    ld = torch.zeros(128, 32, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        svdq_quantize_w4a4_act_fuse_lora_cuda(x.view(1, 4, 128), lora_down=ld)       # 2-D only
+    with pytest.raises(ValueError):
+        svdq_quantize_w4a4_act_fuse_lora_cuda(x, lora_down=None)                      # lora_down is required
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        svdq_quantize_w4a4_act_fuse_lora_cuda(x, lora_down=ld)
+
+
+def test_glue_rejects_cpu_tensors_and_bad_dtypes():
+    x = torch.zeros(4, 64, dtype=torch.bfloat16)
+    for fn in (glue.silu, glue.gelu_new):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            fn(x)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        glue.add(x, x)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        glue.layernorm(x)
+    with pytest.raises(RuntimeError):
+        linearattn_vk_mul_q(x, torch.zeros(1, 2, 33, 32))
+
+
+def test_module_mirror_surface_and_cpu_forward():
+    """Same constructor keywords, parameter names, shapes and dtypes as nunchaku/models/linear.py:13-120."""
+    m = SVDQW4A4Linear(256, 384, rank=32, bias=True, precision="int4", torch_dtype=torch.bfloat16, device="cpu")
+    sd = m.state_dict()
+    assert sd["qweight"].shape == (384, 128) and sd["qweight"].dtype == torch.int8
+    assert sd["wscales"].shape == (256 // 64, 384) and sd["wscales"].dtype == torch.bfloat16
+    assert sd["proj_down"].shape == (256, 32) and sd["proj_up"].shape == (384, 32)
+    assert sd["smooth_factor"].shape == (256,) and sd["bias"].shape == (384,)
+    f = SVDQW4A4Linear(256, 384, rank=16, bias=False, precision="nvfp4", torch_dtype=torch.float16, device="cpu")
+    fs = f.state_dict()
+    assert fs["wscales"].shape == (256 // 16, 384) and fs["wscales"].dtype == torch.float8_e4m3fn
+    assert fs["wcscales"].shape == (384,) and f.wtscale == 1.0 and f.bias is None
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 256, dtype=torch.bfloat16))                             # CPU forward is an error, not a fallback
+
+
+def test_small_helpers():
+    assert ceil_divide(300, 256) == 2 and ceil_divide(256, 256) == 1
+    assert torch_dtype_code(torch.float16) == 0 and torch_dtype_code(torch.bfloat16) == 1
+    with pytest.raises(TypeError):
+        torch_dtype_code(torch.float32)
+    assert get_precision("auto") == "nvfp4" and get_precision("fp4") == "nvfp4" and get_precision("int4") == "int4"
+    assert get_precision("auto", pretrained_model_name_or_path="svdq-int4_r32-flux.1-schnell") == "int4"
+
+    class _L:
+        precision = "nvfp4"
+        out_features = 12288
+
+    assert _fuse_fc1(_L, 256) is True and _fuse_fc1(_L, 4352) is False               # small M fuses, large M splits
