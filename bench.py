@@ -268,25 +268,46 @@ class StackRunner:
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle's reference-emulating mode on a bounded sample of the same workload
 # --------------------------------------------------------------------------------------------
-def cpu_sample(torch, precision: str, reps: int = 1):
-    """One 3072x3072 r=32 SVDQuant linear, M=256 (the text-stream shape; BASELINE config 1) through
-    the CPU oracle in reference-emulating mode.  Returns (seconds per rep, flops per rep)."""
-    from oracle import svdq as O
+class CpuSample:
+    """Bounded CPU sample of the workload: one 3072x3072 r=32 SVDQuant linear on M=256 rows (the text-stream shape, BASELINE
+    config 1) through the oracle's reference-emulating path -- the plain-C restatement oracle/svdq_ref.c on every host
+    thread (OpenMP); the Python restatement if gcc is unavailable."""
 
-    fp4 = precision == "nvfp4"
-    hT = torch.bfloat16
-    layer = O.make_synthetic_layer(DIM, DIM, RANK, fp4=fp4, hT=hT, seed=0)
-    x = O.make_activations(TXT_TOKENS, DIM, hT, seed=1, smooth=layer.smooth)
-    # bounded sample: stop after `reps` repetitions or ~20 s of CPU work, whichever comes first (the INT4
-    # reference-emulating mode walks the 48 groups of the 16-bit accumulation chain: tens of seconds per pass)
-    t0 = time.perf_counter()
-    done = 0
-    while done < reps and (done == 0 or time.perf_counter() - t0 < 20.0):
-        O.svdq_linear_forward(layer, x, mode="ref")
-        done += 1
-    dt = (time.perf_counter() - t0) / done
-    flops = 2 * TXT_TOKENS * DIM * DIM + 2 * TXT_TOKENS * RANK * (DIM + DIM)
-    return dt, flops
+    def __init__(self, torch, precision: str):
+        from oracle import svdq as O
+
+        self.O = O
+        fp4 = precision == "nvfp4"
+        self.layer = O.make_synthetic_layer(DIM, DIM, RANK, fp4=fp4, hT=torch.bfloat16, seed=0)
+        self.x = O.make_activations(TXT_TOKENS, DIM, torch.bfloat16, seed=1, smooth=self.layer.smooth)
+        self.flops = 2 * TXT_TOKENS * DIM * DIM + 2 * TXT_TOKENS * RANK * (DIM + DIM)
+        self.cores = os.cpu_count() or 1
+        try:
+            from oracle import csvdq
+
+            csvdq.build()
+            csvdq.set_threads(self.cores)
+            self.fn = lambda: csvdq.linear_forward(self.layer, self.x)
+            self.impl = "plain-C oracle (oracle/svdq_ref.c, OpenMP)"
+        except Exception as e:  # no gcc on the box: the torch restatement
+            torch.set_num_threads(min(self.cores, 32))
+            self.cores = torch.get_num_threads()
+            self.fn = lambda: O.svdq_linear_forward(self.layer, self.x, mode="ref")
+            self.impl = f"Python oracle (C oracle unavailable: {type(e).__name__})"
+        self.fn()  # warm (page in, OpenMP team start)
+
+    def run(self, budget_s: float):
+        """Repeat the sample for about `budget_s` seconds; returns (seconds per repetition, repetitions)."""
+        t0 = time.perf_counter()
+        reps = 0
+        while reps == 0 or time.perf_counter() - t0 < budget_s:
+            self.fn()
+            reps += 1
+        return (time.perf_counter() - t0) / reps, reps
+
+    def describe(self, precision: str, dt: float, reps: int) -> str:
+        return (f"1 SVDQuant linear 3072x3072 r32 M=256 ({precision}), reference-emulating arithmetic, {self.impl}: "
+                f"{reps} reps x {dt * 1e3:.1f} ms")
 
 
 def run_reference_arm(args):
@@ -295,26 +316,28 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    torch.set_num_threads(min(os.cpu_count() or 1, 32))  # beyond ~32 threads the oracle's small per-group matmuls only contend
     f_main, f_lr = step_flops()
     flops_per_image = (f_main + f_lr) * STEPS_PER_IMAGE
-    times = []
+    cs = CpuSample(torch, args.precision)
+    # a "step" of this arm is a bounded sample: ~4 s of the CPU path, so K + W steps finish within a few minutes
+    times, reps_total = [], 0
     for i in range(args.warmup + args.steps):
-        dt, fl = cpu_sample(torch, args.precision, reps=1)
+        dt_i, reps = cs.run(4.0)
         if i >= args.warmup:
-            times.append(dt)
+            times.append(dt_i)
+            reps_total += reps
     dt = sum(times) / len(times)
-    cpu_flops_s = fl / dt
+    cpu_flops_s = cs.flops / dt
     value = cpu_flops_s / flops_per_image
-    sample = f"1 SVDQuant linear 3072x3072 r32 M=256 ({args.precision}), oracle reference-emulating mode, torch CPU"
+    sample = cs.describe(args.precision, dt, reps_total)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int4" if args.precision == "int4" else "nvfp4",
         "data": "synthetic", "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cs.cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference has no CPU implementation of this path (SURVEY F6); this is the CPU oracle (port); value extrapolates the sample's FLOP rate to one image's hot-path FLOPs",
+        "note": "the reference has no CPU implementation of this path (SURVEY F6); this is the CPU oracle (port) on all host threads; value extrapolates the sample's FLOP rate to one image's hot-path FLOPs",
     }
     _emit(line)
     return 0
@@ -557,11 +580,10 @@ def main() -> int:
     if rank == 0:
         cpu = None
         if not args.skip_cpu and world == 1:   # the CPU baseline is an N=1 figure (rank 0's host cores)
-            torch.set_num_threads(min(os.cpu_count() or 1, 32))
-            dt, fl = cpu_sample(torch, args.precision, reps=3)
-            cpu_v = (fl / dt) / ((f_main + f_lr) * STEPS_PER_IMAGE)
-            cpu = {"value": cpu_v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"1 SVDQuant linear 3072x3072 r32 M=256 ({args.precision}), oracle reference-emulating mode, {dt:.2f} s/rep, <= 3 reps / 20 s"}
+            cs = CpuSample(torch, args.precision)
+            dt, reps = cs.run(10.0)
+            cpu_v = (cs.flops / dt) / ((f_main + f_lr) * STEPS_PER_IMAGE)
+            cpu = {"value": cpu_v, "unit": "images/s", "cores": cs.cores, "kind": "port", "sample": cs.describe(args.precision, dt, reps)}
         line = {
             "metric": METRIC, "value": images_per_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
