@@ -127,69 +127,75 @@ void svdq_linear_ref(int M, int K, int N, int R, int fp4, int bf16, const float 
         free(xs);
     }
 
-    /* NVFP4: decode the 4-bit codes once (values are exact in fp32) */
-    float *adec = NULL, *wdec = NULL;
+    /* NVFP4: decode the activation codes once (values are exact in fp32); weight rows are decoded where they are used */
+    float *adec = NULL;
     if (fp4) {
         adec = (float *)malloc((size_t)M * K * sizeof(float));
-        wdec = (float *)malloc((size_t)N * K * sizeof(float));
 #pragma omp parallel for schedule(static)
         for (long long i = 0; i < (long long)M * K; i++) adec[i] = (float)e2m1_decode(qa[i]);
-#pragma omp parallel for schedule(static)
-        for (long long i = 0; i < (long long)N * K; i++) wdec[i] = (float)e2m1_decode(qw[i]);
     }
 
-#pragma omp parallel for schedule(static)
-    for (int m = 0; m < M; m++) {
+    /* one weight row per iteration, all M activation rows inside: the row of W stays in L1/L2 and the activations (a few MB)
+     * in the shared cache, instead of streaming the whole weight matrix once per activation row */
+#pragma omp parallel
+    {
+        float *wrow = fp4 ? (float *)malloc((size_t)K * sizeof(float)) : NULL;
+#pragma omp for schedule(static)
         for (int n = 0; n < N; n++) {
-            double acc;
-            if (!fp4) {
-                /* acc_hT = fma_hT(hT(int32 p), mul_hT(as, ws), acc_hT) per 64-wide group */
-                float a = 0.f;
-                for (int g = 0; g < G; g++) {
-                    int32_t p = 0;
-                    const int8_t *pa = qa + (size_t)m * K + g * 64, *pw = qw + (size_t)n * K + g * 64;
-                    for (int i = 0; i < 64; i++) p += (int32_t)pa[i] * (int32_t)pw[i];
-                    const float ph = f32_to_ht((float)p, bf16);
-                    const float sc = f64_to_ht((double)as[(size_t)m * G + g] * (double)wscales[(size_t)n * G + g], bf16);
-                    a = f64_to_ht((double)ph * (double)sc + (double)a, bf16);
+            if (fp4)
+                for (int k = 0; k < K; k++) wrow[k] = (float)e2m1_decode(qw[(size_t)n * K + k]);
+            for (int m = 0; m < M; m++) {
+                double acc;
+                if (!fp4) {
+                    /* acc_hT = fma_hT(hT(int32 p), mul_hT(as, ws), acc_hT) per 64-wide group */
+                    float a = 0.f;
+                    for (int g = 0; g < G; g++) {
+                        int32_t p = 0;
+                        const int8_t *pa = qa + (size_t)m * K + g * 64, *pw = qw + (size_t)n * K + g * 64;
+                        for (int i = 0; i < 64; i++) p += (int32_t)pa[i] * (int32_t)pw[i];
+                        const float ph = f32_to_ht((float)p, bf16);
+                        const float sc = f64_to_ht((double)as[(size_t)m * G + g] * (double)wscales[(size_t)n * G + g], bf16);
+                        a = f64_to_ht((double)ph * (double)sc + (double)a, bf16);
+                    }
+                    acc = (double)a;
+                } else {
+                    /* e2m1 x e2m1 products are multiples of 1/4 up to 36: a 16-wide group sums exactly in fp32 */
+                    double s = 0.0;
+                    const float *pa = adec + (size_t)m * K;
+                    for (int g = 0; g < G; g++) {
+                        float sg = 0.f;
+                        for (int i = 0; i < 16; i++) sg += pa[g * 16 + i] * wrow[g * 16 + i];
+                        s += (double)sg * ((double)as[(size_t)m * G + g] * (double)wscales[(size_t)n * G + g]);
+                    }
+                    float a32 = (float)s;
+                    if (alpha != 1.0f) a32 = a32 * alpha;                           /* :341-349 */
+                    acc = (double)f32_to_ht(a32, bf16);                             /* packed_fp32_to_fp16 :351 */
                 }
-                acc = (double)a;
-            } else {
-                /* e2m1 x e2m1 products are multiples of 1/4 up to 36: a 16-wide group sums exactly in fp32 */
-                double s = 0.0;
-                const float *pa = adec + (size_t)m * K, *pw = wdec + (size_t)n * K;
-                for (int g = 0; g < G; g++) {
-                    float sg = 0.f;
-                    for (int i = 0; i < 16; i++) sg += pa[g * 16 + i] * pw[g * 16 + i];
-                    s += (double)sg * ((double)as[(size_t)m * G + g] * (double)wscales[(size_t)n * G + g]);
+                /* EpilogueBias<USE_BIAS, USE_SCALE> */
+                if (wcscales && bias) acc = (double)f64_to_ht(acc * (double)wcscales[n] + (double)bias[n], bf16);
+                else if (wcscales) acc = (double)f64_to_ht(acc * (double)wcscales[n], bf16);
+                else if (bias) acc = (double)f64_to_ht(acc + (double)bias[n], bf16);
+                /* EpilogueLoraUp: hT(lora_act * scale) x lora_up accumulated, fp32 psum -> hT */
+                if (R > 0 && lora_up) {
+                    double add = 0.0;
+                    for (int r = 0; r < R; r++)
+                        add += (double)f32_to_ht(la[(size_t)m * R + r] * 1.0f, bf16) * (double)lora_up[(size_t)n * R + r];
+                    acc = (double)f32_to_ht((float)(acc + add), bf16);
                 }
-                float a32 = (float)s;
-                if (alpha != 1.0f) a32 = a32 * alpha;                           /* :341-349 */
-                acc = (double)f32_to_ht(a32, bf16);                             /* packed_fp32_to_fp16 :351 */
+                float o = (float)acc;
+                if (!bf16) {                                                        /* gemm_base.cuh:688-696 */
+                    if (o > 65504.f) o = 65504.f;
+                    if (o < -65504.f) o = -65504.f;
+                }
+                out[(size_t)m * N + n] = o;
             }
-            /* EpilogueBias<USE_BIAS, USE_SCALE> */
-            if (wcscales && bias) acc = (double)f64_to_ht(acc * (double)wcscales[n] + (double)bias[n], bf16);
-            else if (wcscales) acc = (double)f64_to_ht(acc * (double)wcscales[n], bf16);
-            else if (bias) acc = (double)f64_to_ht(acc + (double)bias[n], bf16);
-            /* EpilogueLoraUp: hT(lora_act * scale) x lora_up accumulated, fp32 psum -> hT */
-            if (R > 0 && lora_up) {
-                double add = 0.0;
-                for (int r = 0; r < R; r++) add += (double)f32_to_ht(la[(size_t)m * R + r] * 1.0f, bf16) * (double)lora_up[(size_t)n * R + r];
-                acc = (double)f32_to_ht((float)(acc + add), bf16);
-            }
-            float o = (float)acc;
-            if (!bf16) {                                                        /* gemm_base.cuh:688-696 */
-                if (o > 65504.f) o = 65504.f;
-                if (o < -65504.f) o = -65504.f;
-            }
-            out[(size_t)m * N + n] = o;
         }
+        free(wrow);
     }
     free(qa);
     free(as);
     free(la);
     free(adec);
-    free(wdec);
 }
 
 /* OpenMP team size for the calls above (torchrun exports OMP_NUM_THREADS=1, which would serialise the CPU arm) */
