@@ -8,7 +8,7 @@ import torch
 
 from .. import repack
 from .._C import NB200_ACT_GELU, NB200_ACT_NONE, NB200_ACT_SILU, NB200_MAX_LORA_SCALES, GemmArgs, check, lib
-from ..utils import torch_dtype_code
+from ..utils import on_device_of, torch_dtype_code
 
 # tuning knobs for experiments (0 = let the launcher choose)
 BLOCK_N_OVERRIDE = 0
@@ -16,6 +16,7 @@ NUM_SMS_OVERRIDE = 0
 PROF_BUFFER = None   # torch int64 tensor [grid, 16]: per-CTA barrier-wait cycle counters (tools/gemm_prof.py)
 
 
+@on_device_of("act")
 def svdq_gemm_w4a4_cuda(
     act: torch.Tensor,
     wgt: torch.Tensor,
@@ -197,6 +198,7 @@ def svdq_gemm_w4a4_cuda(
                                   out_linearattn.shape[0], out_linearattn.shape[1], N, torch.cuda.current_stream().cuda_stream), "litela_vk")
 
 
+@on_device_of("q")
 def linearattn_vk_mul_q(q: torch.Tensor, vk: torch.Tensor) -> None:
     """``kernels::linearattn_vk_mul_q`` (src/kernels/zgemm/gemm_w4a4.cu:107-111): in place on ``q`` [B, tokens, heads * 32]
     (or [B, tokens, heads, 32]) with ``vk`` float32 [B, heads, 33, 32]; eps = 1e-6 as in the reference launcher."""

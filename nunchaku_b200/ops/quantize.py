@@ -7,9 +7,10 @@ import torch
 
 from .. import repack
 from .._C import QuantizeArgs, check, lib
-from ..utils import ceil_divide, torch_dtype_code
+from ..utils import ceil_divide, on_device_of, torch_dtype_code
 
 
+@on_device_of("input")
 def svdq_quantize_w4a4_act_fuse_lora_cuda(
     input: torch.Tensor,
     output: torch.Tensor | None = None,

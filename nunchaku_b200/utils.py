@@ -1,6 +1,8 @@
 """Host helpers mirroring nunchaku/utils.py for the SVDQuant path on B200."""
 from __future__ import annotations
 
+import functools
+
 import torch
 
 
@@ -40,3 +42,22 @@ def torch_dtype_code(dtype: torch.dtype) -> int:
     if dtype == torch.bfloat16:
         return 1
     raise TypeError(f"SVDQuant W4A4 runs in float16 or bfloat16, got {dtype}")
+
+
+def on_device_of(arg_name: str, position: int = 0):
+    """Decorator: run the op with the CUDA device of the named tensor argument current, so that ``torch.cuda.current_stream()``
+    and the kernel launch refer to the device that owns the pointers (the reference's ops take the device from their tensors
+    the same way, src/interop/torch.cpp:84-91).  CPU / missing tensors fall through to the op's own error handling."""
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            t = kwargs.get(arg_name, args[position] if len(args) > position else None)
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return fn(*args, **kwargs)
+            return fn(*args, **kwargs)
+
+        return wrapper
+
+    return deco

