@@ -1,0 +1,307 @@
+// Drop-in definitions of the reference's zgemm.h hot-path functions on top of libnunchaku_b200.so.
+//
+// A maintainer of the reference replaces
+//     src/kernels/zgemm/gemm_w4a4.cu + gemm_w4a4_launch_*.cu          (setup.py:176-183)
+// by this one file (and links -lnunchaku_b200): it defines, with the reference's own signatures
+// (src/kernels/zgemm/zgemm.h:8-46),
+//     nunchaku::kernels::gemm_w4a4, ::quantize_w4a4_act_fuse_lora, ::linearattn_vk_mul_q
+// so that src/Linear.cpp, src/FluxModel.cpp, src/SanaModel.cpp and nunchaku/csrc/* compile and link UNCHANGED.
+// It is compiled against the reference's headers (Tensor.h, common.h, zgemm.h) -- see oracle/ref_build/build_ref.sh,
+// which links it with the reference's untouched src/Linear.cpp into oracle/_ref/libnunchaku_seam.so;
+// tests/test_gpu_seam.py drives GEMM_W4A4::forward / forward_quant / the fused MLP / the 10-argument QKV forward
+// through it and compares with the reference's own kernels on the same B200.
+//
+// Weight-side tensors arrive in the checkpoint (mma.sync fragment) layout and are converted
+// once per parameter by the nb200_repack_* kernels; the converted copies live in a cache keyed on the parameter's
+// device address, shape and dtype.  The reference mutates parameters in place (Module::loadParam -> Tensor::copy_)
+// and re-allocates some (lora_*, wcscales, lazy-load / offload: src/Linear.cpp:124-154, src/Module.h:96-131), so the
+// loader must drop stale entries: call nunchaku::kernels::b200_invalidate(dst) at the end of GEMM_W4A4::loadParam
+// (one line), or b200_invalidate_all() after a load_state_dict / LoRA update.
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "Tensor.h"
+#include "common.h"
+#include "kernels/zgemm/zgemm.h"
+#include "nunchaku_b200.h"
+
+namespace nunchaku::kernels {
+
+namespace {
+
+int dtype_of(const Tensor &t) {
+    if (t.scalar_type() == Tensor::BF16) return NB200_BF16;
+    if (t.scalar_type() == Tensor::FP16) return NB200_FP16;
+    throw std::invalid_argument("nunchaku_b200: fp16 / bf16 tensor expected");
+}
+void check(int st, const char *what) {
+    if (st != NB200_OK) throw std::runtime_error(std::string(what) + ": " + nb200_last_error());
+}
+
+// ---- repack cache -------------------------------------------------------------------------------------------------
+struct Key {
+    const void *ptr;
+    int kind;
+    int device;
+    bool operator==(const Key &o) const { return ptr == o.ptr && kind == o.kind && device == o.device; }
+};
+struct KeyHash {
+    size_t operator()(const Key &k) const { return std::hash<const void *>()(k.ptr) ^ (size_t(k.kind) << 1) ^ (size_t(k.device) << 9); }
+};
+struct Entry {
+    std::vector<int> shape;
+    int dtype = 0;
+    const void *dep = nullptr;  // lora_up depends on the cscale vector it was divided by
+    float mul = 1.f;
+    void *data = nullptr;
+    size_t bytes = 0;
+};
+enum Kind { K_QWEIGHT, K_QWEIGHT_FP4, K_WSCALES, K_WSCALES_FP4, K_VEC_F32, K_VEC_HT, K_LORA_UP, K_LORA_DOWN, K_LORA_DOWN_NEXT, K_CONST };
+
+std::mutex g_mu;
+std::unordered_map<Key, Entry, KeyHash> g_cache;
+struct Workspace {
+    void *ptr = nullptr;
+    long long bytes = 0;
+};
+std::unordered_map<int, Workspace> g_workspace;  // per device, zero-initialised once (nb200_quantize_args.workspace)
+
+int current_device() {
+    int d = 0;
+    checkCUDA(cudaGetDevice(&d));
+    return d;
+}
+
+// Returns the cached converted copy of `src` or builds it with `make(dst)`.
+template <typename Make>
+void *cached(const Tensor &src, int kind, size_t bytes, const void *dep, float mul, Make &&make) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    const Key key{src.data_ptr(), kind, current_device()};
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) {
+        Entry &e = it->second;
+        if (e.shape == src.shape.dataExtent && e.dtype == int(src.scalar_type()) && e.dep == dep && e.mul == mul && e.bytes == bytes) return e.data;
+        cudaFree(e.data);  // same address, different tensor: rebuild
+        g_cache.erase(it);
+    }
+    Entry e;
+    e.shape = src.shape.dataExtent;
+    e.dtype = int(src.scalar_type());
+    e.dep = dep;
+    e.mul = mul;
+    e.bytes = bytes;
+    checkCUDA(cudaMalloc(&e.data, bytes ? bytes : 1));
+    make(e.data);
+    g_cache.emplace(key, e);
+    return e.data;
+}
+
+void *stream() { return getCurrentCUDAStream(); }
+
+const void *b_qweight(const Tensor &w, bool fp4) {
+    const int N = w.shape[0], K = w.shape[1] * 2;
+    return cached(w, fp4 ? K_QWEIGHT_FP4 : K_QWEIGHT, size_t(N) * K / 2, nullptr, 1.f,
+                  [&](void *dst) { check(nb200_repack_qweight(w.data_ptr(), dst, N, K, fp4, stream()), "nb200_repack_qweight"); });
+}
+const void *b_wscales(const Tensor &ws, int N, int K, bool fp4) {
+    if (fp4)
+        return cached(ws, K_WSCALES_FP4, size_t(N) * K / 16, nullptr, 1.f,
+                      [&](void *dst) { check(nb200_repack_wscales_fp4(ws.data_ptr(), dst, N, K, stream()), "nb200_repack_wscales_fp4"); });
+    return cached(ws, K_WSCALES, size_t(N) * K / 64 * 2, nullptr, 1.f,
+                  [&](void *dst) { check(nb200_repack_wscales_int4(ws.data_ptr(), dst, N, K, stream()), "nb200_repack_wscales_int4"); });
+}
+const float *b_vec_f32(const Tensor &v, float mul) {
+    const int n = int(v.numel());
+    return static_cast<const float *>(cached(v, K_VEC_F32, size_t(n) * 4, nullptr, mul, [&](void *dst) {
+        check(nb200_repack_channel_vector(v.data_ptr(), dst, n, dtype_of(v), 1, mul, stream()), "nb200_repack_channel_vector");
+    }));
+}
+const void *b_vec_ht(const Tensor &v) {
+    const int n = int(v.numel());
+    return cached(v, K_VEC_HT, size_t(n) * 2, nullptr, 1.f,
+                  [&](void *dst) { check(nb200_repack_channel_vector(v.data_ptr(), dst, n, dtype_of(v), 0, 1.f, stream()), "nb200_repack_channel_vector"); });
+}
+// alpha without per-channel scales: a constant vector per (N, alpha), keyed on the weight tensor
+const float *b_const(const Tensor &owner, int N, float value) {
+    return static_cast<const float *>(cached(owner, K_CONST, size_t(N) * 4, nullptr, value, [&](void *dst) {
+        std::vector<float> h(N, value);
+        checkCUDA(cudaMemcpyAsync(dst, h.data(), size_t(N) * 4, cudaMemcpyHostToDevice, getCurrentCUDAStream()));
+        checkCUDA(cudaStreamSynchronize(getCurrentCUDAStream()));  // h dies at scope exit
+    }));
+}
+const void *b_lora_up(const Tensor &lu, const float *cscale) {
+    const int N = lu.shape[0], R = lu.shape[1], Rp = (R + 31) / 32 * 32;
+    return cached(lu, K_LORA_UP, size_t(N) * Rp * 2, cscale, 1.f,
+                  [&](void *dst) { check(nb200_repack_lora_up(lu.data_ptr(), dst, cscale, N, R, dtype_of(lu), stream()), "nb200_repack_lora_up"); });
+}
+const void *b_lora_down(const Tensor &ld) {
+    const int K = ld.shape[0], R = ld.shape[1], Rp = (R + 31) / 32 * 32;
+    return cached(ld, K_LORA_DOWN, size_t(2) * K * Rp * 2, nullptr, 1.f,
+                  [&](void *dst) { check(nb200_repack_lora_down(ld.data_ptr(), dst, K, R, dtype_of(ld), stream()), "nb200_repack_lora_down"); });
+}
+const void *b_lora_down_next(const Tensor &ld) {
+    const int K = ld.shape[0], R = ld.shape[1];
+    return cached(ld, K_LORA_DOWN_NEXT, size_t(K) * R * 2, nullptr, 1.f,
+                  [&](void *dst) { check(nb200_repack_lora_down_next(ld.data_ptr(), dst, K, R, dtype_of(ld), stream()), "nb200_repack_lora_down_next"); });
+}
+
+Workspace quantize_workspace(int Mp, int K) {
+    const long long need = nb200_quantize_workspace_bytes(Mp, K);
+    std::lock_guard<std::mutex> lock(g_mu);
+    Workspace &w = g_workspace[current_device()];
+    if (need > w.bytes) {
+        // grow: the old buffer may still be in use by queued launches -> device-wide sync before freeing (rare: first calls only)
+        if (w.ptr) {
+            checkCUDA(cudaDeviceSynchronize());
+            checkCUDA(cudaFree(w.ptr));
+        }
+        const long long bytes = std::max<long long>(need, 1 << 20);
+        checkCUDA(cudaMalloc(&w.ptr, bytes));
+        checkCUDA(cudaMemset(w.ptr, 0, bytes));
+        w.bytes = bytes;
+    }
+    return w;
+}
+
+}  // namespace
+
+// ---- cache control (the one addition to the reference's interface) -----------------------------------------------------
+void b200_invalidate(Tensor t) {
+    if (!t.valid() && !t.buffer) return;
+    std::lock_guard<std::mutex> lock(g_mu);
+    const void *p = t.data_ptr();
+    for (auto it = g_cache.begin(); it != g_cache.end();) {
+        if (it->first.ptr == p) {
+            cudaFree(it->second.data);
+            it = g_cache.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+void b200_invalidate_all() {
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto &kv : g_cache) cudaFree(kv.second.data);
+    g_cache.clear();
+}
+
+// ---- zgemm.h:39-46 -------------------------------------------------------------------------------------------------
+void quantize_w4a4_act_fuse_lora(Tensor input, Tensor output, Tensor oscales, Tensor lora_down, Tensor lora_act_out, Tensor smooth,
+                                 bool fuse_glu, bool fp4) {
+    nb200_quantize_args a{};
+    a.M = int(input.numel() / input.shape[-1]);
+    a.Mp = int(output.numel() / output.shape[-1]);
+    a.K = input.shape[-1] / (fuse_glu ? 2 : 1);
+    a.R = lora_down.valid() ? lora_down.shape[1] : 0;
+    a.input = input.data_ptr();
+    a.output = output.data_ptr();
+    a.oscales = oscales.data_ptr();
+    a.lora_act_out = (a.R > 0) ? lora_act_out.data_ptr<float>() : nullptr;
+    a.lora_down = (a.R > 0) ? b_lora_down(lora_down) : nullptr;
+    a.smooth = smooth.valid() ? b_vec_ht(smooth) : nullptr;
+    a.dtype = dtype_of(input);
+    a.fuse_glu = fuse_glu;
+    a.fp4 = fp4;
+    Workspace w = quantize_workspace(a.Mp, a.K);
+    a.workspace = w.ptr;
+    a.workspace_bytes = w.bytes;
+    check(nb200_quantize_w4a4_act_fuse_lora(&a, stream()), "nb200_quantize_w4a4_act_fuse_lora");
+}
+
+// ---- zgemm.h:8-36 --------------------------------------------------------------------------------------------------
+void gemm_w4a4(Tensor act, Tensor wgt, Tensor out, Tensor qout, Tensor ascales, Tensor wscales, Tensor oscales, Tensor poolout,
+               Tensor lora_act_in, Tensor lora_up, Tensor lora_down, Tensor lora_act_out, Tensor norm_q, Tensor norm_k, Tensor rotary_emb,
+               Tensor bias, Tensor smooth_factor, Tensor out_vk, Tensor out_linearattn, bool act_unsigned, std::vector<float> lora_scales,
+               bool fuse_silu, bool fp4, float alpha, Tensor wcscales, Tensor out_q, Tensor out_k, Tensor out_v, int attn_tokens) {
+    (void)poolout;  // accepted and ignored, as in the reference (gemm_w4a4_launch_impl.cuh:356-367)
+    nb200_gemm_args a{};
+    a.Mp = int(act.numel() / act.shape[-1]);
+    a.K = act.shape[-1] * 2;
+    a.N = wgt.shape[0];
+    a.act = act.data_ptr();
+    a.ascales = ascales.data_ptr();
+    a.wgt = b_qweight(wgt, fp4);
+    a.wscales = b_wscales(wscales, a.N, a.K, fp4);
+    const float *cs = nullptr;
+    if (wcscales.valid() && wcscales.numel() > 0)
+        cs = b_vec_f32(wcscales, alpha);
+    else if (alpha != 1.0f)
+        cs = b_const(wgt, a.N, alpha);
+    a.cscale = cs;
+    a.bias = bias.valid() ? b_vec_f32(bias, 1.0f) : nullptr;
+    if (lora_up.valid() && lora_up.shape[1] > 0) {
+        a.R_up = lora_up.shape[1];
+        a.lora_up = b_lora_up(lora_up, cs);
+        a.lora_act_in = lora_act_in.data_ptr<float>();
+    }
+    for (size_t i = 0; i < NB200_MAX_LORA_SCALES; i++) a.lora_scales[i] = i < lora_scales.size() ? lora_scales[i] : 0.f;
+
+    // dtype: zgemm gemm_w4a4.cu:63-73
+    Tensor::ScalarType st = Tensor::INVALID_SCALAR_TYPE;
+    if (!fp4) {
+        st = ascales.dtype();
+    } else {
+        for (const Tensor &t : {out, bias, lora_up, lora_down, poolout, wcscales})
+            if (t.valid()) st = t.dtype();
+    }
+    a.dtype = st == Tensor::BF16 ? NB200_BF16 : NB200_FP16;
+    a.fp4 = fp4;
+    a.act_unsigned = act_unsigned;
+    a.mid_act = fuse_silu ? NB200_ACT_SILU : NB200_ACT_NONE;
+
+    Tensor scratch;  // SANA LiteLA: plain projection into an L2-resident scratch, reduced by nb200_litela_vk
+    const bool litela = out_vk.valid();
+    if (litela) {
+        scratch = Tensor::allocate({a.Mp, a.N}, st, act.device());
+        out = scratch;
+    }
+    if (qout.valid()) {  // fc1 -> GELU -> quantise for fc2 (launch_impl:282-310)
+        a.qout = qout.data_ptr();
+        a.oscales = oscales.data_ptr();
+        a.smooth_next = b_vec_ht(smooth_factor);
+        if (lora_down.valid() && lora_down.shape[1] > 0) {
+            a.R_down = lora_down.shape[1];
+            a.lora_down_next = b_lora_down_next(lora_down);
+            a.lora_act_out = lora_act_out.data_ptr<float>();
+        }
+    } else if (rotary_emb.valid() && out_q.valid()) {  // RMSNorm + RoPE + PackQKV (launch_impl:376-393)
+        a.out_q = out_q.data_ptr();
+        a.out_k = out_k.data_ptr();
+        a.out_v = out_v.data_ptr();
+        a.stride_head_q = (long long)out_q.stride(1);
+        a.stride_head_k = (long long)out_k.stride(1);
+        a.stride_head_v = (long long)out_v.stride(1);
+        a.attn_tokens = attn_tokens;
+    } else {
+        a.out = out.data_ptr();
+        a.M_out = int(out.numel() / out.shape[-1]);
+        a.N_out = out.shape[-1];
+    }
+    if (rotary_emb.valid()) {
+        a.norm_q = norm_q.data_ptr();
+        a.norm_k = norm_k.data_ptr();
+        a.rotary_emb = rotary_emb.data_ptr<float>();
+    }
+    check(nb200_gemm_w4a4(&a, stream()), "nb200_gemm_w4a4");
+    if (litela) {
+        const int batch = out_linearattn.shape[0], tokens = out_linearattn.shape[1];
+        check(nb200_litela_vk(a.dtype, scratch.data_ptr(), out_linearattn.data_ptr(), out_vk.data_ptr<float>(), batch, tokens, a.N, stream()),
+              "nb200_litela_vk");
+    }
+}
+
+// ---- zgemm.h:37 ----------------------------------------------------------------------------------------------------
+void linearattn_vk_mul_q(Tensor q, Tensor vk) {
+    const int batch = vk.shape[0], heads = vk.shape[1];
+    const int tokens = int(q.numel() / (size_t(batch) * heads * 32));
+    check(nb200_linearattn_vk_mul_q(dtype_of(q), q.data_ptr(), vk.data_ptr<float>(), batch, tokens, heads, 1e-6f, stream()), "nb200_linearattn_vk_mul_q");
+}
+
+// not reachable from Linear.cpp / FluxModel.cpp / SanaModel.cpp; kept so every zgemm.h W4A4 symbol resolves
+void quantize_w4a4_act(Tensor, Tensor, Tensor) { throw std::runtime_error("quantize_w4a4_act: unused by the reference's models; not provided"); }
+void quantize_w4a4_wgt(Tensor, Tensor, Tensor) { throw std::runtime_error("quantize_w4a4_wgt: offline tool; not provided"); }
+void set_faster_i2f_mode(std::string) {}  // sm_75-only switch (zgemm.h:77)
+
+}  // namespace nunchaku::kernels

@@ -36,6 +36,15 @@ __all__ = [
     "pack_lowrank",
     "unpack_lowrank",
     "pack_rotemb",
+    "ref_act_flat_index",
+    "pack_ref_act",
+    "unpack_ref_act",
+    "ref_ascale_flat_index",
+    "pack_ref_ascales",
+    "unpack_ref_ascales",
+    "ref_lora_act_flat_index",
+    "pack_ref_lora_act",
+    "unpack_ref_lora_act",
 ]
 
 
@@ -237,3 +246,112 @@ def pack_rotemb(sin: torch.Tensor, cos: torch.Tensor) -> torch.Tensor:
     out = torch.empty(M * 128, dtype=torch.float32, device=sin.device)
     out[idx.reshape(-1)] = torch.stack([sin, cos], dim=-1).to(torch.float32).reshape(-1)
     return out.view(M, 128)
+
+
+# --------------------------------------------------------------------------------------
+# A.4  The reference's INTER-OP tensors (INT4 path): what its quantizer / fused epilogue write and
+#   its GEMM reads.  Ours are laid out differently (include/nunchaku_b200.h); these maps exist so
+#   that outputs of the reference's kernels RUN ON THE B200 (oracle/_ref, tests/golden/ref_gpu_*.npz)
+#   can be compared element by element with the oracle.  Pinned by tests/test_ref_gpu_golden.py:
+#   a wrong formula would scramble ~100 % of the codes, the goldens agree to <= 2e-3.
+#
+#   act     uint4 [Mp/256][K/64][warp 8][mt 2][lane 32], components {x,y,z,w} =
+#           (row g, k t*8+r) (row g+8, k t*8+r) (row g, k 32+t*8+r) (row g+8, k 32+t*8+r), nibble r
+#           (quantize_w4a4_from_fpsum_warp gemm_w4a4.cuh:429-523, store :1002, load_act gemm_base.cuh:266-276)
+#   ascales hT    [Mp/256][K/64][warp 8][lane 16][2]: row (lane/8)*16 + lane%8 + 8*e of the warp's 32
+#           (pack_ascales gemm_base.cuh:452-468, load_ascale :296-312)
+#   lora_act f32  [Mp/256][R/16][warp 8][mt 2][j 8][lane 32]: m16n8k16 C fragments, j = 4*nhalf + 2*h + e ->
+#           row g + 8*h, rank column 8*nhalf + 2*t + e     (lora.cuh:61-94, mma gemm_base.cuh:203-227)
+# --------------------------------------------------------------------------------------
+def ref_act_flat_index(Mp: int, K: int, device=None) -> tuple[torch.Tensor, torch.Tensor]:
+    """(uint32 word index, nibble) of logical (m, k) inside the reference's packed activation tensor."""
+    assert Mp % 256 == 0 and K % 64 == 0, (Mp, K)
+    m = torch.arange(Mp, device=device).view(Mp, 1)
+    k = torch.arange(K, device=device).view(1, K)
+    bm, m_in = m // 256, m % 256
+    warp, mt, h, g = m_in // 32, (m_in % 32) // 16, (m_in % 16) // 8, m_in % 8
+    kt, k_in = k // 64, k % 64
+    c, t, r = k_in // 32, (k_in % 32) // 8, k_in % 8
+    lane = g * 4 + t
+    word = ((((bm * (K // 64) + kt) * 8 + warp) * 2 + mt) * 32 + lane) * 4 + (c * 2 + h)
+    return word.expand(Mp, K), r.expand(Mp, K)
+
+
+def pack_ref_act(codes: torch.Tensor) -> torch.Tensor:
+    """codes: integer [Mp, K] (low 4 bits kept) -> uint8 [Mp, K/2] in the reference's activation order."""
+    Mp, K = codes.shape
+    word, nib = ref_act_flat_index(Mp, K, codes.device)
+    vals = (codes.to(torch.int64) & 0xF) << (4 * nib.to(torch.int64))
+    words = torch.zeros(Mp * K // 8, dtype=torch.int64, device=codes.device)
+    words.scatter_add_(0, word.reshape(-1), vals.reshape(-1))
+    b = torch.stack([(words >> (8 * i)) & 0xFF for i in range(4)], dim=-1).to(torch.uint8)
+    return b.reshape(Mp, K // 2)
+
+
+def unpack_ref_act(packed: torch.Tensor, signed: bool = True) -> torch.Tensor:
+    """uint8/int8 [Mp, K/2] written by the reference's quantizer -> int8 [Mp, K] codes."""
+    Mp, Kh = packed.shape
+    K = Kh * 2
+    b = packed.contiguous().view(torch.uint8).reshape(-1, 4).to(torch.int64)
+    words = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16) | (b[:, 3] << 24)
+    word, nib = ref_act_flat_index(Mp, K, packed.device)
+    v = (words[word.reshape(-1)] >> (4 * nib.reshape(-1).to(torch.int64))) & 0xF
+    if signed:
+        v = torch.where(v >= 8, v - 16, v)
+    return v.reshape(Mp, K).to(torch.int8)
+
+
+def ref_ascale_flat_index(Mp: int, G: int, device=None) -> torch.Tensor:
+    """flat element index of logical (m, group) in the reference's packed activation scales."""
+    assert Mp % 256 == 0
+    m = torch.arange(Mp, device=device).view(Mp, 1)
+    grp = torch.arange(G, device=device).view(1, G)
+    bm, m_in = m // 256, m % 256
+    warp, r32 = m_in // 32, m_in % 32
+    lane = (r32 // 16) * 8 + r32 % 8
+    e = (r32 % 16) // 8
+    return (((bm * G + grp) * 8 + warp) * 16 + lane) * 2 + e
+
+
+def pack_ref_ascales(scales_mg: torch.Tensor) -> torch.Tensor:
+    """logical [Mp, G] -> nominal [G, Mp] in the reference's order."""
+    Mp, G = scales_mg.shape
+    idx = ref_ascale_flat_index(Mp, G, scales_mg.device).reshape(-1)
+    out = torch.empty(Mp * G, dtype=scales_mg.dtype, device=scales_mg.device)
+    out[idx] = scales_mg.reshape(-1)
+    return out.view(G, Mp)
+
+
+def unpack_ref_ascales(packed: torch.Tensor) -> torch.Tensor:
+    """nominal [G, Mp] written by the reference -> logical [Mp, G]."""
+    G, Mp = packed.shape
+    idx = ref_ascale_flat_index(Mp, G, packed.device)
+    return packed.reshape(-1)[idx.reshape(-1)].view(Mp, G)
+
+
+def ref_lora_act_flat_index(Mp: int, R: int, device=None) -> torch.Tensor:
+    """flat f32 index of logical (m, r) in the reference's low-rank hidden state."""
+    assert Mp % 256 == 0 and R % 16 == 0
+    m = torch.arange(Mp, device=device).view(Mp, 1)
+    r = torch.arange(R, device=device).view(1, R)
+    bm, m_in = m // 256, m % 256
+    warp, mt, h, g = m_in // 32, (m_in % 32) // 16, (m_in % 16) // 8, m_in % 8
+    rt, r_in = r // 16, r % 16
+    nhalf, t, e = r_in // 8, (r_in % 8) // 2, r_in % 2
+    j = nhalf * 4 + h * 2 + e
+    lane = g * 4 + t
+    return ((((bm * (R // 16) + rt) * 8 + warp) * 2 + mt) * 8 + j) * 32 + lane
+
+
+def pack_ref_lora_act(la: torch.Tensor) -> torch.Tensor:
+    Mp, R = la.shape
+    idx = ref_lora_act_flat_index(Mp, R, la.device).reshape(-1)
+    out = torch.empty(Mp * R, dtype=la.dtype, device=la.device)
+    out[idx] = la.reshape(-1)
+    return out.view(Mp, R)
+
+
+def unpack_ref_lora_act(packed: torch.Tensor) -> torch.Tensor:
+    Mp, R = packed.shape
+    idx = ref_lora_act_flat_index(Mp, R, packed.device)
+    return packed.reshape(-1)[idx.reshape(-1)].view(Mp, R)
