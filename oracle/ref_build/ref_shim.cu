@@ -49,6 +49,12 @@ typedef struct nref_tensor {
 const char *nref_last_error(void);
 }
 
+#ifdef NREF_SEAM_BUILD
+namespace nunchaku::kernels {
+void b200_invalidate_all();  // nunchaku_b200/csrc/seam/zgemm_b200.cpp: what a maintainer calls from GEMM_W4A4::loadParam
+}
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -228,6 +234,9 @@ int nref_linear_load(void *h, const char *key, const nref_tensor *src, void *str
         p.key = key;
         p.t = wrap(src);
         static_cast<GEMM_W4A4 *>(h)->loadParams(p, /*partial=*/true);
+#ifdef NREF_SEAM_BUILD
+        nunchaku::kernels::b200_invalidate_all();  // parameters changed in place: drop the converted copies
+#endif
     });
 }
 int nref_linear_lora_rank(void *h) { return static_cast<GEMM_W4A4 *>(h)->lora_rank; }
