@@ -1,19 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- FLUX.1-schnell 1024x1024 4-step, SVDQuant W4A4 + low-rank linear stack on B200.
+"""bench.py -- FLUX.1-schnell 1024x1024 4-step: the SVDQuant W4A4 + low-rank hot path of every transformer block on B200.
 
-A "step" is one denoising step's worth of the hot path: every SVDQuant linear of the
-FLUX.1-schnell transformer (19 joint blocks x {qkv, out, fc1, fc2} for the 4096-token image
-stream and the 256-token text stream, 38 single blocks x {qkv, out, fc1, fc2} on 4352 tokens)
-= 304 fused W4A4 GEMM launches + 228 activation-quantize launches when fc2's input is quantised inside fc1's GEMM
-epilogue as in the reference (the 256-token text stream); the large-M MLPs run as plain GEMM + GELU followed by the
-quantizer (57 more quantize launches, faster on B200 -- DESIGN.md 4.4; NB200_BENCH_SPLIT_MLP=0 fuses them all), at the model's exact shapes,
-rank 32, synthetic random-init 4-bit weights (no checkpoints offline) and synthetic activations.
-Attention / AdaLN / elementwise glue are outside the hot path and not run.
-An image is 4 steps.  value = images/s of this stack, whole job over all ranks.
+A "step" is one denoising step's worth of the hot path, CHAINED the way the model chains it:
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision int4|nvfp4] [--impl reference]
+    joint block (x19), image stream (4096 tokens) and text stream (256 tokens) each:
+        LayerNorm -> QKV projection with RMSNorm(Q,K) + RoPE in the GEMM epilogue -> [attention: NOT run, out of scope]
+        -> out projection -> LayerNorm -> fc1 -> GELU -> fc2 (fc2's 4-bit input produced by fc1's epilogue / the split route) -> add
+    single block (x38), 4352 tokens: LayerNorm -> QKV(+RMSNorm+RoPE) -> out projection ; fc1 -> GELU -> fc2 ; add
 
-JSON keys follow the driver contract (+ roofline, cpu_baseline, e2e, clocks, gpu_launches).
+= 304 fused W4A4 GEMM launches + the activation quantizers + the LayerNorm / add glue kernels (row a14), at the model's
+exact shapes, rank 32, random-init 4-bit weights in the reference's checkpoint layout (no checkpoints offline).  Every layer
+reads its predecessor's output; the out projection reads the first M x 3072 elements of the QKV result as the stand-in for
+the attention output.  Attention itself and the AdaLN modulation GEMVs are outside the hot path and not run.
+An image is 4 steps.  value = images/s of this stack, whole job over all ranks (replicas, no collective in the timed path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision nvfp4|int4] [--impl reference]
+
+One JSON line on stdout (driver contract + roofline, cpu_baseline, e2e, clocks, gpu_launches, reference_gpu, cublas_bf16).
 """
 from __future__ import annotations
 
@@ -28,40 +31,53 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DIM, MLP, RANK = 3072, 12288, 32
+DIM, MLP, RANK, HEADS = 3072, 12288, 32, 24
 IMG_TOKENS, TXT_TOKENS = 4096, 256
 N_JOINT, N_SINGLE = 19, 38
 STEPS_PER_IMAGE = 4
+METRIC = "FLUX.1-schnell 1024px 4-step images/sec (SVDQuant W4A4+LR linear stack)"
 
-# (name, K, N, activation)
-BLOCK_LINEARS = [("qkv", DIM, 3 * DIM, "none"), ("out", DIM, DIM, "none"), ("fc1", DIM, MLP, "gelu"), ("fc2", MLP, DIM, "none")]
+# (name, K, N)
+BLOCK_LINEARS = [("qkv", DIM, 3 * DIM), ("out", DIM, DIM), ("fc1", DIM, MLP), ("fc2", MLP, DIM)]
+
+
+def block_list():
+    """[(tag, M)] stream-blocks of one denoising step in execution order; each runs the four linears of BLOCK_LINEARS."""
+    blocks = []
+    for b in range(N_JOINT):
+        blocks.append((f"joint{b}.img", IMG_TOKENS))
+        blocks.append((f"joint{b}.txt", TXT_TOKENS))
+    for b in range(N_SINGLE):
+        blocks.append((f"single{b}", IMG_TOKENS + TXT_TOKENS))
+    return blocks
 
 
 def layer_list():
-    """[(tag, M, K, N, act)] for one denoising step, in execution order."""
-    layers = []
-    for b in range(N_JOINT):
-        for stream, M in (("img", IMG_TOKENS), ("txt", TXT_TOKENS)):
-            for name, K, N, act in BLOCK_LINEARS:
-                layers.append((f"joint{b}.{stream}.{name}", M, K, N, act))
-    for b in range(N_SINGLE):
-        for name, K, N, act in BLOCK_LINEARS:
-            layers.append((f"single{b}.{name}", IMG_TOKENS + TXT_TOKENS, K, N, act))
-    return layers
+    """[(tag, M, K, N)] for one denoising step, in execution order (304 linears)."""
+    return [(f"{tag}.{name}", M, K, N) for tag, M in block_list() for name, K, N in BLOCK_LINEARS]
 
 
 def step_flops():
     f_main = f_lr = 0
-    for _, M, K, N, _ in layer_list():
+    for _, M, K, N in layer_list():
         f_main += 2 * M * K * N
         f_lr += 2 * M * RANK * (K + N)
     return f_main, f_lr
 
 
 def gemm_bytes(M, K, N, R, fp4):
+    """algorithmic bytes of one fused GEMM launch"""
     G, s = (16, 1) if fp4 else (64, 2)
     Mp = (M + 255) // 256 * 256
     return Mp * K // 2 + (K // G) * Mp * s + N * K // 2 + (K // G) * N * s + 4 * Mp * R + 2 * N * R + 4 * N + 2 * M * N
+
+
+def host_threads() -> int:
+    """threads this process may actually use (cgroup / affinity aware), not os.cpu_count()"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
 
 
 # --------------------------------------------------------------------------------------------
@@ -77,8 +93,7 @@ class ClockSampler:
         self._t = None
 
     def _run_nvml(self) -> bool:
-        """Fast path: NVML polled every 20 ms (the timed region of a default run is ~0.2 s; nvidia-smi alone takes ~0.1 s per
-        query).  Same fields as the nvidia-smi query.  Returns False when NVML is unusable so that nvidia-smi takes over."""
+        """NVML polled every 20 ms (the timed region of a default run is ~0.2 s; nvidia-smi alone takes ~0.1 s per query)."""
         try:
             import pynvml as nv
 
@@ -135,143 +150,256 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# synthetic FLUX.1-schnell linear stack on the GPU (reference-layout random parameters)
+# the FLUX.1-schnell block stack on the GPU (reference-layout random parameters)
 # --------------------------------------------------------------------------------------------
-def build_stack(torch, precision: str, dtype, device):
+def make_linear(torch, K, N, precision, dtype, device, g, act_unsigned=False):
     from nunchaku_b200.models.linear import SVDQW4A4Linear
 
     fp4 = precision == "nvfp4"
-    g = torch.Generator(device=device).manual_seed(1234)
-    mods = []
-    for tag, M, K, N, act in layer_list():
+    m = SVDQW4A4Linear(K, N, rank=RANK, bias=True, precision=precision, torch_dtype=dtype, device=device, act_unsigned=act_unsigned)
+    with torch.no_grad():
+        # the packed layouts are permutations: random bytes in the reference layout ARE random weights
+        m.qweight.copy_(torch.randint(-128, 128, m.qweight.shape, generator=g, device=device, dtype=torch.int8))
+        if fp4:
+            m.wscales.copy_(torch.randint(0x30, 0x38, m.wscales.shape, generator=g, device=device, dtype=torch.uint8).view(torch.float8_e4m3fn))  # 0.5 .. 0.94
+            m.wtscale = 1.0 / (2.6 * 0.72 * K ** 0.5)
+            m.wcscales.copy_((1.0 + 0.05 * torch.randn(N, generator=g, device=device)).to(dtype))
+        else:
+            m.wscales.copy_(((0.75 + 0.5 * torch.rand(m.wscales.shape, generator=g, device=device)) / (4.6 * K ** 0.5)).to(dtype))
+        m.bias.copy_((0.1 * torch.randn(N, generator=g, device=device)).to(dtype))
+        m.smooth_factor.copy_((0.75 + 0.5 * torch.rand(K, generator=g, device=device)).to(dtype))
+        m.proj_down.copy_((torch.randn(K, RANK, generator=g, device=device) / K ** 0.5).to(dtype))
+        m.proj_up.copy_((0.1 * torch.randn(N, RANK, generator=g, device=device) / RANK ** 0.5).to(dtype))
+    m.invalidate()
+    return m
+
+
+class Block:
+    def __init__(self, torch, tag, M, precision, dtype, device, g):
+        fp4 = precision == "nvfp4"
+        self.tag, self.M = tag, M
+        self.qkv = make_linear(torch, DIM, 3 * DIM, precision, dtype, device, g)
+        self.out = make_linear(torch, DIM, DIM, precision, dtype, device, g)
+        self.fc1 = make_linear(torch, DIM, MLP, precision, dtype, device, g)
         # fc2 consumes the fused fc1 epilogue's UNSIGNED (shifted GELU) INT4 activations (attention.py:98-99)
-        m = SVDQW4A4Linear(K, N, rank=RANK, bias=True, precision=precision, torch_dtype=dtype, device=device,
-                           act_unsigned=(tag.endswith("fc2") and not fp4))
-        with torch.no_grad():
-            # the packed layouts are permutations: random bytes in the reference layout ARE random weights
-            m.qweight.copy_(torch.randint(-128, 128, m.qweight.shape, generator=g, device=device, dtype=torch.int8))
-            if fp4:
-                # ue4m3 codes 0x30..0x37 = 0.5 .. 0.9375
-                m.wscales.copy_(torch.randint(0x30, 0x38, m.wscales.shape, generator=g, device=device, dtype=torch.uint8).view(torch.float8_e4m3fn))
-                m.wtscale = 1.0 / (2.6 * 0.72 * K ** 0.5)
-                m.wcscales.copy_((1.0 + 0.05 * torch.randn(N, generator=g, device=device)).to(dtype))
-            else:
-                m.wscales.copy_(((0.75 + 0.5 * torch.rand(m.wscales.shape, generator=g, device=device)) / (4.6 * K ** 0.5)).to(dtype))
-            m.bias.copy_((0.1 * torch.randn(N, generator=g, device=device)).to(dtype))
-            m.smooth_factor.copy_((0.75 + 0.5 * torch.rand(K, generator=g, device=device)).to(dtype))
-            m.proj_down.copy_((torch.randn(K, RANK, generator=g, device=device) / K ** 0.5).to(dtype))
-            m.proj_up.copy_((0.1 * torch.randn(N, RANK, generator=g, device=device) / RANK ** 0.5).to(dtype))
-        mods.append((tag, M, K, N, act, m))
-    return mods
+        self.fc2 = make_linear(torch, MLP, DIM, precision, dtype, device, g, act_unsigned=not fp4)
+        self.norm_q = (1.0 + 0.1 * torch.randn(128, generator=g, device=device)).to(dtype)
+        self.norm_k = (1.0 + 0.1 * torch.randn(128, generator=g, device=device)).to(dtype)
+
+    def linears(self):
+        return [self.qkv, self.out, self.fc1, self.fc2]
 
 
 class StackRunner:
-    """Runs the 304 linears of one step through the public ops (quantize + GEMM)."""
+    """One denoising step of the hot path through the package's public module / ops API."""
 
-    def __init__(self, torch, mods, dtype, device):
-        from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
-        from nunchaku_b200.ops.quantize import svdq_quantize_w4a4_act_fuse_lora_cuda
+    def __init__(self, torch, precision, dtype, device):
+        from nunchaku_b200.ops import fused, glue
+        from nunchaku_b200.utils import pack_rotemb
 
-        self.torch, self.mods = torch, mods
-        self.gemm, self.quant = svdq_gemm_w4a4_cuda, svdq_quantize_w4a4_act_fuse_lora_cuda
-        g = torch.Generator(device=device).manual_seed(99)
-        # fixed, well-conditioned inputs per (M, K); outputs per (M, N); quantize scratch per (M, K)
-        self.x, self.y, self.q = {}, {}, {}
-        for _, M, K, N, act, m in mods:
-            if (M, K) not in self.x:
-                x = torch.randn(M, K, generator=g, device=device)
-                if K == MLP:
-                    x = torch.nn.functional.gelu(x, approximate="tanh")
-                self.x[(M, K)] = x.to(dtype)
-                Mp = (M + 255) // 256 * 256
-                fp4 = m.precision == "nvfp4"
-                self.q[(M, K)] = (
-                    torch.empty(Mp, K // 2, dtype=torch.uint8, device=device),
-                    torch.empty(K // 16, Mp, dtype=torch.float8_e4m3fn, device=device) if fp4
-                    else torch.empty(K // 64, Mp, dtype=dtype, device=device),
-                    torch.empty(Mp, RANK, dtype=torch.float32, device=device),
-                )
-            if (M, N) not in self.y:
-                self.y[(M, N)] = torch.empty(M, N, dtype=dtype, device=device)
-        # NVFP4 MLP intermediate [M, 12288] for the large-M path (fc1 plain GEMM + GELU -> quantizer -> fc2)
-        self.hidden = {M: torch.empty(M, MLP, dtype=dtype, device=device) for M in {mm for _, mm, _, _, _, _ in mods} if M >= 2048}
-        self.split_mlp = os.environ.get("NB200_BENCH_SPLIT_MLP", "1") != "0"
-        self.gemm_events = None
+        self.torch, self.glue, self.fused = torch, glue, fused
+        self.precision, self.dtype, self.device = precision, dtype, device
+        g = torch.Generator(device=device).manual_seed(1234)
+        self.blocks = [Block(torch, tag, M, precision, dtype, device, g) for tag, M in block_list()]
+        for b in self.blocks:   # convert once, then drop the checkpoint-layout copies of the big tensors (weights.py)
+            for lin in b.linears():
+                lin.release_reference_layout()
+        # packed RoPE tables (reference pack_rotemb layout) per token count, real sin / cos of random angles
+        self.rot = {}
+        for M in (IMG_TOKENS, TXT_TOKENS, IMG_TOKENS + TXT_TOKENS):
+            Mp = (M + 255) // 256 * 256
+            ang = torch.rand(Mp, 64, generator=g, device=device) * 6.2831853
+            self.rot[M] = pack_rotemb(torch.sin(ang), torch.cos(ang))
+        self.h_img = torch.randn(IMG_TOKENS, DIM, generator=g, device=device).to(dtype)
+        self.h_txt = torch.randn(TXT_TOKENS, DIM, generator=g, device=device).to(dtype)
+        self.result = torch.empty(IMG_TOKENS + TXT_TOKENS, DIM, dtype=dtype, device=device)
         self.launches = 0
 
     def set_inputs(self, img, txt):
-        """e2e: refresh the step's inputs (the image/text stream activations)."""
-        self.x[(IMG_TOKENS, DIM)].copy_(img, non_blocking=True)
-        self.x[(TXT_TOKENS, DIM)].copy_(txt, non_blocking=True)
+        self.h_img.copy_(img, non_blocking=True)
+        self.h_txt.copy_(txt, non_blocking=True)
 
-    def step(self, record_gemm_events=False):
-        """qkv, out: quantize + GEMM.  fc1 -> fc2: quantize + fused GEMM (GELU, fc2's low-rank down
-        projection and fc2's 4-bit activations produced in fc1's epilogue; the [M, 12288] tensor never
-        reaches HBM) + GEMM -- the reference's launch structure (FluxModel.cpp:16-20): 304 GEMMs and 228
-        quantizes per step."""
+    def _stream_block(self, b: Block, h):
+        """LayerNorm -> QKV(+RMSNorm+RoPE epilogue) -> [attention not run] -> out ; LayerNorm -> fc1 -> GELU -> fc2 ; add"""
+        glue, M = self.glue, b.M
+        n1 = glue.layernorm(h, None, None, 1e-6)
+        qkv = b.qkv.forward_qkv(n1, b.norm_q, b.norm_k, self.rot[M])
+        attn = qkv.view(-1)[: M * DIM].view(M, DIM)            # stand-in for the attention output: freshly written, L2-hot
+        o = b.out.forward(attn.view(1, M, DIM)).view(M, DIM)
+        n2 = n1 if b.tag.startswith("single") else glue.layernorm(o, None, None, 1e-6)
+        fuse = self.fused._fuse_fc1(b.fc1, M)
+        f = b.fc1.forward_mlp(n2, b.fc2, fuse=fuse)
+        self.launches += 1 + 2 + 2 + (0 if n2 is n1 else 1) + (3 if fuse else 4) + 1
+        return glue.add(o, f)
+
+    def step(self):
         torch = self.torch
-        ev = [] if record_gemm_events else None
-
-        def timed(fn, flops):
-            if ev is None:
-                fn()
-                return
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            ev.append((e0, e1, flops))
-
-        mods = self.mods
+        h_img, h_txt = self.h_img, self.h_txt
         i = 0
-        while i < len(mods):
-            tag, M, K, N, act, m = mods[i]
-            q, s, la = self.q[(M, K)]
-            fp4 = m.precision == "nvfp4"
-            self.quant(self.x[(M, K)], output=q, oscales=s, lora_down=m.proj_down, lora_act_out=la,
-                       smooth=m.smooth_factor, fp4=fp4)
-            self.launches += 1
-            if tag.endswith("fc1"):
-                _, _, K2, N2, _, m2 = mods[i + 1]
-                q2, s2, la2 = self.q[(M, K2)]
-                if M >= 2048 and self.split_mlp:
-                    # large M: plain 256-wide GEMM with GELU + the activation quantizer beats the fused launch
-                    # (nunchaku_b200.ops.fused._fuse_fc1, DESIGN.md section 4.4); one more quantize launch, same arithmetic
-                    hid = self.hidden[M]
-                    timed(lambda: self.gemm(act=q, wgt=m.qweight, out=hid, ascales=s, wscales=m.wscales, lora_act_in=la, lora_up=m.proj_up,
-                                            bias=m.bias, fp4=fp4, alpha=m.wtscale, wcscales=m.wcscales, fuse_gelu=True),
-                          2 * M * K * N + 2 * M * RANK * N)
-                    self.quant(hid, output=q2, oscales=s2, lora_down=m2.proj_down, lora_act_out=la2, smooth=m2.smooth_factor, fp4=fp4,
-                               shift_unsigned=not fp4)
-                    self.launches += 1
-                else:
-                    timed(lambda: self.gemm(act=q, wgt=m.qweight, qout=q2, ascales=s, wscales=m.wscales, oscales=s2,
-                                            lora_act_in=la, lora_up=m.proj_up, lora_down=m2.proj_down, lora_act_out=la2,
-                                            bias=m.bias, smooth_factor=m2.smooth_factor, fp4=fp4, alpha=m.wtscale,
-                                            wcscales=m.wcscales), 2 * M * K * N + 2 * M * RANK * N + 2 * M * RANK * N)
-                timed(lambda: self.gemm(act=q2, wgt=m2.qweight, out=self.y[(M, N2)], ascales=s2, wscales=m2.wscales,
-                                        lora_act_in=la2, lora_up=m2.proj_up, bias=m2.bias, fp4=fp4, alpha=m2.wtscale,
-                                        wcscales=m2.wcscales, act_unsigned=m2.act_unsigned),
-                      2 * M * K2 * N2 + 2 * M * RANK * N2)
-                self.launches += 2
-                i += 2
-            else:
-                timed(lambda: self.gemm(act=q, wgt=m.qweight, out=self.y[(M, N)], ascales=s, wscales=m.wscales,
-                                        lora_act_in=la, lora_up=m.proj_up, bias=m.bias, fp4=fp4, alpha=m.wtscale,
-                                        wcscales=m.wcscales), 2 * M * K * N + 2 * M * RANK * N)
-                self.launches += 1
-                i += 1
-        self.gemm_events = ev
-        return self.y[(IMG_TOKENS + TXT_TOKENS, DIM)]
+        for _ in range(N_JOINT):
+            h_img = self._stream_block(self.blocks[i], h_img)
+            h_txt = self._stream_block(self.blocks[i + 1], h_txt)
+            i += 2
+        h = torch.cat([h_img, h_txt], dim=0)      # one copy per step (the model concatenates the streams here too)
+        for _ in range(N_SINGLE):
+            h = self._stream_block(self.blocks[i], h)
+            i += 1
+        self.result.copy_(h)
+        return self.result
+
+
+class GemmRecorder:
+    """Records every fused-GEMM call of one eager step (arguments kept alive) so that the GEMMs alone can be replayed from
+    a CUDA graph: the roofline of the dominant kernel is measured under the same replay conditions as the step."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __enter__(self):
+        import nunchaku_b200.models.linear as L
+
+        self.L, self.orig = L, L.gemm_b200
+
+        def rec(*a, **k):
+            self.calls.append((a, k))
+            return self.orig(*a, **k)
+
+        L.gemm_b200 = rec
+        return self
+
+    def __exit__(self, *exc):
+        self.L.gemm_b200 = self.orig
+
+    def flops(self):
+        total = 0
+        for a, k in self.calls:
+            w = a[3]
+            rows = a[0].shape[0]
+            out = k.get("out")
+            M = out.shape[0] if out is not None else rows
+            total += 2 * M * w.K * w.N + 2 * M * w.rank * w.N
+            if k.get("next_w") is not None:
+                total += 2 * M * k["next_w"].rank * w.N
+        return total
+
+    def replay(self):
+        for a, k in self.calls:
+            self.orig(*a, **k)
+
+
+def capture(torch, fn):
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    graph.replay()
+    torch.cuda.synchronize()
+    return graph
+
+
+def time_replays(torch, graph, n, barrier):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        graph.replay()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm: the oracle's reference-emulating mode on a bounded sample of the same workload
+# comparison legs on the same GPU
 # --------------------------------------------------------------------------------------------
+def cublas_bf16_leg(torch, device, steps):
+    """The 16-bit ceiling: the same 304 GEMM shapes as plain bf16 cuBLAS matmuls on de-quantised weights
+    (random bf16 of the same shapes; no low-rank branch, no epilogue), CUDA-graph replay."""
+    shapes = {}
+    for _, M, K, N in layer_list():
+        shapes[(M, K, N)] = shapes.get((M, K, N), 0) + 1
+    g = torch.Generator(device=device).manual_seed(7)
+    ops = []
+    for (M, K, N), cnt in shapes.items():
+        x = torch.randn(M, K, generator=g, device=device).to(torch.bfloat16)
+        ws = [torch.randn(N, K, generator=g, device=device).to(torch.bfloat16) for _ in range(min(cnt, 8))]   # > L2 in total
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=device)
+        ops.append((x, ws, y, cnt))
+
+    def run():
+        for x, ws, y, cnt in ops:
+            for i in range(cnt):
+                torch.matmul(x, ws[i % len(ws)].t(), out=y)
+
+    graph = capture(torch, run)
+    ms = time_replays(torch, graph, steps, torch.cuda.synchronize) / steps
+    f_main, _ = step_flops()
+    return {"ms_per_step": ms, "tflops": f_main / (ms * 1e-3) / 1e12, "what": "304 torch.matmul (cuBLAS) bf16 GEMMs of the same shapes, graph replay"}
+
+
+def reference_gpu_leg(torch, device):
+    """The REFERENCE's own INT4 kernels (oracle/_ref/libnunchaku_ref.so = its unmodified sources built for sm_100a,
+    oracle/ref_build/build_ref.sh) timed on this GPU per distinct layer shape (quantize + GEMM through its C++ class
+    GEMM_W4A4, and the fused fc1->fc2 MLP), CUDA events, summed with the step's multiplicities.  NVFP4 cannot run: the
+    reference's NVFP4 kernels need sm_120a."""
+    try:
+        from oracle import refgpu as R   # test / comparison infrastructure: never on the product path
+    except Exception as e:
+        return {"unavailable": f"oracle.refgpu import failed: {e!r}"}
+    if not R.available("ref"):
+        return {"unavailable": "oracle/_ref/libnunchaku_ref.so not built (oracle/ref_build/build_ref.sh needs /root/reference)"}
+    dtype = torch.bfloat16
+    g = torch.Generator(device=device).manual_seed(3)
+
+    def ref_lin(K, N):
+        m = R.RefLinear(K, N, bias=True, fp4=False, dtype=dtype)
+        m.load(qweight=torch.randint(-128, 128, (N, K // 2), generator=g, device=device, dtype=torch.int8),
+               wscales=((0.75 + 0.5 * torch.rand(K // 64, N, generator=g, device=device)) / (4.6 * K ** 0.5)).to(dtype),
+               bias=(0.1 * torch.randn(N, generator=g, device=device)).to(dtype),
+               smooth=(0.75 + 0.5 * torch.rand(K, generator=g, device=device)).to(dtype),
+               lora_down=(torch.randn(K, RANK, generator=g, device=device) / K ** 0.5).to(dtype),
+               lora_up=(0.1 * torch.randn(N, RANK, generator=g, device=device) / RANK ** 0.5).to(dtype))
+        return m
+
+    def t_ms(fn, iters=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    per = {}
+    total = 0.0
+    counts = {}
+    for _, M in block_list():
+        counts[M] = counts.get(M, 0) + 1
+    qkv, out, fc1, fc2 = ref_lin(DIM, 3 * DIM), ref_lin(DIM, DIM), ref_lin(DIM, MLP), ref_lin(MLP, DIM)
+    for M, cnt in counts.items():
+        x = torch.randn(M, DIM, generator=g, device=device).to(dtype)
+        nq = torch.ones(128, dtype=dtype, device=device)
+        rot = torch.zeros(1, (M + 255) // 256 * 256, 128, dtype=torch.float32, device=device)
+        t = {"qkv_rope": t_ms(lambda: qkv.forward_qkv(x, nq, nq, rot)), "out": t_ms(lambda: out.forward(x)),
+             "mlp_fused": t_ms(lambda: fc1.forward_mlp(fc2, x))}
+        per[str(M)] = {k: round(v, 3) for k, v in t.items()}
+        total += cnt * sum(t.values())
+    f_main, f_lr = step_flops()
+    return {"ms_per_step": total, "value": (1.0 / STEPS_PER_IMAGE) / (total * 1e-3), "unit": "images/s", "precision": "int4",
+            "tflops": (f_main + f_lr) / (total * 1e-3) / 1e12, "per_shape_ms": per,
+            "what": "reference kernels (unmodified sources, sm_100a build) through its C++ GEMM_W4A4 class: quantize + GEMM per layer, fused fc1->fc2; "
+                    "CUDA events per distinct shape x multiplicity in the step; LayerNorm / add glue not included"}
+
+
 class CpuSample:
     """Bounded CPU sample of the workload: one 3072x3072 r=32 SVDQuant linear on M=256 rows (the text-stream shape, BASELINE
-    config 1) through the oracle's reference-emulating path -- the plain-C restatement oracle/svdq_ref.c on every host
-    thread (OpenMP); the Python restatement if gcc is unavailable."""
+    config 1) through the oracle's reference-emulating path -- the plain-C restatement oracle/svdq_ref.c (pinned bit-exact
+    against the reference's GPU kernels via tests/test_ref_gpu_golden.py) on the host threads this process may use."""
 
     def __init__(self, torch, precision: str):
         from oracle import svdq as O
@@ -281,7 +409,7 @@ class CpuSample:
         self.layer = O.make_synthetic_layer(DIM, DIM, RANK, fp4=fp4, hT=torch.bfloat16, seed=0)
         self.x = O.make_activations(TXT_TOKENS, DIM, torch.bfloat16, seed=1, smooth=self.layer.smooth)
         self.flops = 2 * TXT_TOKENS * DIM * DIM + 2 * TXT_TOKENS * RANK * (DIM + DIM)
-        self.cores = os.cpu_count() or 1
+        self.cores = host_threads()
         try:
             from oracle import csvdq
 
@@ -297,7 +425,6 @@ class CpuSample:
         self.fn()  # warm (page in, OpenMP team start)
 
     def run(self, budget_s: float):
-        """Repeat the sample for about `budget_s` seconds; returns (seconds per repetition, repetitions)."""
         t0 = time.perf_counter()
         reps = 0
         while reps == 0 or time.perf_counter() - t0 < budget_s:
@@ -306,48 +433,42 @@ class CpuSample:
         return (time.perf_counter() - t0) / reps, reps
 
     def describe(self, precision: str, dt: float, reps: int) -> str:
-        return (f"1 SVDQuant linear 3072x3072 r32 M=256 ({precision}), reference-emulating arithmetic, {self.impl}: "
-                f"{reps} reps x {dt * 1e3:.1f} ms")
+        return (f"1 SVDQuant linear 3072x3072 r32 M=256 ({precision}), reference-emulating arithmetic, {self.impl}, {self.cores} threads "
+                f"(sched_getaffinity): {reps} reps x {dt * 1e3:.1f} ms")
 
 
 def run_reference_arm(args):
     import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
     f_main, f_lr = step_flops()
     flops_per_image = (f_main + f_lr) * STEPS_PER_IMAGE
     cs = CpuSample(torch, args.precision)
-    # a "step" of this arm is a bounded sample: ~4 s of the CPU path, so K + W steps finish within a few minutes
     times, reps_total = [], 0
-    for i in range(args.warmup + args.steps):
+    for i in range(args.warmup + args.steps):   # a "step" of this arm is a bounded ~4 s sample of the CPU path
         dt_i, reps = cs.run(4.0)
         if i >= args.warmup:
             times.append(dt_i)
             reps_total += reps
     dt = sum(times) / len(times)
-    cpu_flops_s = cs.flops / dt
-    value = cpu_flops_s / flops_per_image
+    value = (cs.flops / dt) / flops_per_image
     sample = cs.describe(args.precision, dt, reps_total)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int4" if args.precision == "int4" else "nvfp4",
-        "data": "synthetic", "config": workload_config(args),
+    _emit({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int4" if args.precision == "int4" else "nvfp4", "data": "synthetic", "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cs.cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference has no CPU implementation of this path (SURVEY F6); this is the CPU oracle (port) on all host threads; value extrapolates the sample's FLOP rate to one image's hot-path FLOPs",
-    }
-    _emit(line)
+        "note": "the reference has no CPU implementation of this path (SURVEY F6); this is the CPU oracle (port, pinned to the reference's GPU kernels) "
+                "on the host threads; value extrapolates the sample's FLOP rate to one image's hot-path FLOPs",
+    })
     return 0
 
 
-METRIC = "FLUX.1-schnell 1024px 4-step images/sec (SVDQuant W4A4+LR linear stack)"
-
-
 def workload_config(args):
-    return {"workload": "FLUX.1-schnell 1024x1024 4-step bs=1: 304 SVDQuant linears/step (19 joint x (img 4096 + txt 256 tokens) + 38 single x 4352 tokens), dim 3072, mlp 12288, rank 32",
+    return {"workload": "FLUX.1-schnell 1024x1024 4-step bs=1: per step 304 SVDQuant linears (19 joint x (img 4096 + txt 256 tokens) + 38 single x 4352 "
+                        "tokens; dim 3072, mlp 12288, rank 32, 24 heads) chained through LayerNorm / RMSNorm+RoPE epilogue / GELU-quantise / add; attention not run",
             "precision": args.precision, "parallelism": f"replica x{args.gpus}",
             "l2": "inputs larger than L2 (4.3 GB of 4-bit weights streamed per step)"}
 
@@ -356,9 +477,8 @@ _REAL_STDOUT = None
 
 
 def _quiet_stdout() -> None:
-    """stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints "NCCL version ..." on
-    stdout when NCCL_DEBUG is set in the environment).  Point fd 1 at stderr for the run and keep the real stdout for
-    the final line."""
+    """stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL banner): point fd 1 at stderr for
+    the run and keep the real stdout for the final line."""
     global _REAL_STDOUT
     if _REAL_STDOUT is None:
         sys.stdout.flush()
@@ -376,6 +496,18 @@ def _emit(line: dict) -> None:
         sys.stdout.flush()
 
 
+def load_peaks():
+    """roofline denominators: tensor-pipe peaks measured on a B200 by tools/ubench/mma_peak.cu (committed: profiles/r02_mma_peaks.json)
+    and the driver's MEASURED_PEAKS.json (HBM, cuBLAS bf16)."""
+    peaks = {}
+    for name in ("MEASURED_PEAKS.json", os.path.join("profiles", "r02_mma_peaks.json")):
+        try:
+            peaks.update(json.load(open(os.path.join(ROOT, name))))
+        except Exception:
+            pass
+    return peaks
+
+
 def main() -> int:
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -383,11 +515,11 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    # NVFP4 is what the reference itself selects on Blackwell (nunchaku/utils.py:190-231 -> "fp4" for sm_12x; its INT4
-    # mma.sync.s4 is emulated on sm_100) and the only 4-bit format tcgen05 runs natively; the INT4 path
-    # (16-bit tensor pipe after an in-kernel dequant) is measured in the same run and reported under "secondary".
+    # NVFP4 is what the reference itself selects on Blackwell (nunchaku/utils.py:190-231 -> "fp4" for sm_12x; its INT4 mma.sync.s4 is
+    # emulated on sm_100) and the only 4-bit format tcgen05 runs natively; INT4 is measured in the same run ("secondary").
     ap.add_argument("--precision", default=os.environ.get("NB200_BENCH_PRECISION", "nvfp4"), choices=["int4", "nvfp4"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the other precision's device-resident measurement")
+    ap.add_argument("--no-legs", action="store_true", help="skip the cuBLAS-bf16 and reference-GPU comparison legs")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
@@ -407,77 +539,55 @@ def main() -> int:
 
     check(lib.nb200_check_device(), "check_device")
     dtype = torch.bfloat16
-    mods = build_stack(torch, args.precision, dtype, device)
-    runner = StackRunner(torch, mods, dtype, device)
-    n_layers = len(mods)
+    runner = StackRunner(torch, args.precision, dtype, device)
 
     def barrier():
         torch.cuda.synchronize()
         replica.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also triggers the one-time repack) -----------------------------------------
+    # ---- warm-up ----------------------------------------------------------------------------------
     for _ in range(args.warmup):
         runner.launches = 0
         runner.step()
-    launches_per_step = runner.launches   # our kernels only (quantize + gemm; the fused fc1 memset is a driver memset node)
+    launches_per_step = runner.launches   # our kernels only (quantize, GEMM, LayerNorm, add); memsets / the one cat+copy per step are not counted
     torch.cuda.synchronize()
 
-    # ---- device-resident throughput: captured CUDA graph of one step ---------------------------
+    # ---- device-resident throughput: captured CUDA graph of one step ---------------------------------
     graph = None
     if not args.no_graph:
         try:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                runner.step()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=s):
-                    runner.step()
-            torch.cuda.current_stream().wait_stream(s)
-            graph.replay()
-            torch.cuda.synchronize()
+            graph = capture(torch, runner.step)
         except Exception as e:  # pragma: no cover
             print(f"[bench] CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
             graph = None
 
-    def one_step():
-        if graph is not None:
-            graph.replay()
-        else:
+    class Eager:
+        def replay(self):
             runner.step()
 
+    stepper = graph if graph is not None else Eager()
     with ClockSampler(local) as clocks:
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            one_step()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-    ms_total = replica.max_over_ranks(ms, device)
-    ms_per_step = ms_total / args.steps
+        ms = time_replays(torch, stepper, args.steps, barrier)
+    ms_per_step = replica.max_over_ranks(ms, device) / args.steps
     images_per_s = world * (1.0 / STEPS_PER_IMAGE) / (ms_per_step * 1e-3)
     f_main, f_lr = step_flops()
+    clk = clocks.summary()
 
-    # ---- e2e through the public API with HOST buffers --------------------------------------------
+    # ---- e2e through the public API with HOST buffers ---------------------------------------------------
     img_h = torch.randn(IMG_TOKENS, DIM).to(dtype).pin_memory()
     txt_h = torch.randn(TXT_TOKENS, DIM).to(dtype).pin_memory()
     out_h = torch.empty(IMG_TOKENS + TXT_TOKENS, DIM, dtype=dtype).pin_memory()
     h2d = img_h.numel() * 2 + txt_h.numel() * 2
     d2h = out_h.numel() * 2
-    # Every step copies its inputs host -> device and its result device -> host.  The copies run on a second stream through
-    # double-buffered device staging tensors, so step i+1's upload and step i's download overlap step i's / i+1's kernels (what a
-    # serving loop does); the kernels themselves are the same per-layer launches through the public ops as in `runner.step()`.
+    # Every step copies its inputs host -> device and its result device -> host on a second stream through double-buffered
+    # staging tensors, so step i+1's upload and step i's download overlap the kernels (what a serving loop does).
     copy_s = torch.cuda.Stream()
     st_img = [torch.empty(IMG_TOKENS, DIM, dtype=dtype, device=device) for _ in range(2)]
     st_txt = [torch.empty(TXT_TOKENS, DIM, dtype=dtype, device=device) for _ in range(2)]
     st_out = [torch.empty(IMG_TOKENS + TXT_TOKENS, DIM, dtype=dtype, device=device) for _ in range(2)]
-    up_done = [torch.cuda.Event() for _ in range(2)]      # staging[b] holds the inputs of the step that will read it
-    up_free = [torch.cuda.Event() for _ in range(2)]      # the compute stream has consumed staging[b]
-    dn_ready = [torch.cuda.Event() for _ in range(2)]     # st_out[b] holds a finished step's result
-    dn_done = [torch.cuda.Event() for _ in range(2)]      # ... and it has reached the host
+    up_done, up_free = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+    dn_ready, dn_done = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
 
     def upload(b):
         with torch.cuda.stream(copy_s):
@@ -495,18 +605,13 @@ def main() -> int:
         for i in range(n):
             b = i & 1
             cur.wait_event(up_done[b])
-            runner.x[(IMG_TOKENS, DIM)].copy_(st_img[b], non_blocking=True)      # device -> device, microseconds
-            runner.x[(TXT_TOKENS, DIM)].copy_(st_txt[b], non_blocking=True)
+            runner.set_inputs(st_img[b], st_txt[b])      # device -> device, microseconds
             up_free[b].record(cur)
             if i + 1 < n:
                 upload(b ^ 1)
-            if graph is not None:   # the same per-layer op calls, captured once (outputs are preallocated: the ops are graph-safe)
-                graph.replay()
-                y = runner.y[(IMG_TOKENS + TXT_TOKENS, DIM)]
-            else:
-                y = runner.step()
-            cur.wait_event(dn_done[b])                                           # st_out[b] was downloaded two steps ago
-            st_out[b].copy_(y, non_blocking=True)
+            stepper.replay()
+            cur.wait_event(dn_done[b])                    # st_out[b] was downloaded two steps ago
+            st_out[b].copy_(runner.result, non_blocking=True)
             dn_ready[b].record(cur)
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(dn_ready[b])
@@ -522,61 +627,66 @@ def main() -> int:
     e2e_s = time.perf_counter() - t0
     e2e_images = world * (1.0 / STEPS_PER_IMAGE) / (replica.max_over_ranks(e2e_s, device) / args.steps)
 
-    # ---- roofline of the dominant kernel (fused GEMM), CUDA events on the launch stream ------------
-    runner.step(record_gemm_events=True)
+    # ---- roofline of the dominant kernel (fused GEMM): the step's 304 GEMM launches alone, graph replay, CUDA events ------------
+    with GemmRecorder() as rec:
+        runner.step()
     torch.cuda.synchronize()
-    g_ms = sum(a.elapsed_time(b) for a, b, _ in runner.gemm_events)
-    g_fl = sum(f for _, _, f in runner.gemm_events)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured bf16_tflops_sustained (MEASURED_PEAKS.json)" if peaks else "fallback 1.4 PF sustained"
-    mult = 4.0 if args.precision == "nvfp4" else 1.0
+    g_graph = capture(torch, rec.replay)
+    g_ms = time_replays(torch, g_graph, args.steps, torch.cuda.synchronize) / args.steps
+    g_fl = rec.flops()
+    n_gemm = len(rec.calls)
+    peaks = load_peaks()
+    fp4 = args.precision == "nvfp4"
+    key = "nvf4_cg2" if fp4 else "bf16_cg1"
+    if key in peaks:
+        # burst figure when the run's median clock sat near the maximum, sustained (power-limited clocks) otherwise
+        near_max = clk["sm_mhz"] is not None and clk["sm_max_mhz"] and clk["sm_mhz"] >= 0.9 * clk["sm_max_mhz"]
+        which = "tflops_burst" if near_max else "tflops_sustained"
+        peak = float(peaks[key][which])
+        peak_basis = f"{key}.{which} measured by tools/ubench/mma_peak.cu on a B200 (profiles/r02_mma_peaks.json); run median SM clock {clk['sm_mhz']} MHz"
+    else:
+        peak = float(peaks.get("bf16_tflops", 1746.5)) * (4.0 if fp4 else 1.0)
+        peak_basis = "fallback: MEASURED_PEAKS.json bf16_tflops" + (" x4" if fp4 else "")
     achieved = g_fl / (g_ms * 1e-3) / 1e12
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch on the primary shape (M=4096, K=N=3072, r=32), from the
-    # committed `ncu --set full` captures profiles/r01x_gemm_{int4,nvfp4}_ncu.txt (the 25 MB output stays in L2)
+    # dram bytes of ONE launch on the primary shape (M=4096, K=N=3072, r=32) from the committed `ncu --set full` captures (profiles/)
     traffic = {"int4": 12.5e6, "nvfp4": 13.2e6}[args.precision]
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak * mult, "unit": "TFLOP/s",
-                "frac": achieved / (bf16_peak * mult), "traffic": traffic,
-                "traffic_basis": "bytes per launch, primary shape 4096x3072x3072, ncu r01x (algorithmic: 37.6 MB incl. the 25 MB output that stays in L2)",
-                "kernel": "gemm_w4a4_kernel", "launches": len(runner.gemm_events),
-                "avg_launch_us": g_ms * 1e3 / len(runner.gemm_events),
-                "peak_basis": peak_src + (" x4 (FP4 pipe = 4x the 16-bit pipe)" if mult == 4.0 else " (INT4 runs on the 16-bit pipe: tcgen05 has no INT4 kind)")}
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_basis": "bytes per launch, primary shape 4096x3072x3072, ncu (algorithmic: 37.6 MB incl. the 25 MB output that stays in L2)",
+                "kernel": "gemm_nvfp4_cluster_kernel" if fp4 else "gemm_w4a4_kernel", "launches": n_gemm, "avg_launch_us": g_ms * 1e3 / n_gemm,
+                "timing": "the step's GEMM launches alone, CUDA-graph replay, CUDA events on the launch stream", "peak_basis": peak_basis,
+                "gemm_share_of_step": g_ms / ms_per_step}
+    del g_graph, rec
 
-    # ---- the other 4-bit format, device-resident graph replay only (same step, same timing rules) ----------
+    # ---- comparison legs on the same GPU (rank 0, N=1) --------------------------------------------------------
+    legs = {}
+    if not args.no_legs and world == 1:
+        try:
+            legs["cublas_bf16"] = cublas_bf16_leg(torch, device, args.steps)
+        except Exception as e:  # pragma: no cover
+            legs["cublas_bf16"] = {"unavailable": repr(e)}
+        try:
+            legs["reference_gpu"] = reference_gpu_leg(torch, device)
+        except Exception as e:
+            legs["reference_gpu"] = {"unavailable": repr(e)}
+
+    # ---- the other 4-bit format, device-resident graph replay only ---------------------------------------------
     secondary = None
     timing_mode = "cuda graph replay" if graph is not None else "eager launches"
     if not args.no_secondary:
-        other = "int4" if args.precision == "nvfp4" else "nvfp4"
-        graph = None  # release the captured graph's memory pool
-        runner2 = StackRunner(torch, build_stack(torch, other, dtype, device), dtype, device)
+        other = "int4" if fp4 else "nvfp4"
+        del graph, stepper
+        runner2 = StackRunner(torch, other, dtype, device)
         for _ in range(args.warmup):
             runner2.step()
         torch.cuda.synchronize()
-        s2 = torch.cuda.Stream()
-        s2.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s2):
-            runner2.step()
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, stream=s2):
-                runner2.step()
-        torch.cuda.current_stream().wait_stream(s2)
-        g2.replay()
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(args.steps):
-            g2.replay()
-        a1.record()
-        barrier()
-        ms2 = replica.max_over_ranks(a0.elapsed_time(a1), device) / args.steps
+        g2 = capture(torch, runner2.step)
+        ms2 = replica.max_over_ranks(time_replays(torch, g2, args.steps, barrier), device) / args.steps
         secondary = {"precision": other, "ms_per_step": ms2, "value": world * (1.0 / STEPS_PER_IMAGE) / (ms2 * 1e-3), "unit": "images/s",
                      "tflops": world * (f_main + f_lr) / (ms2 * 1e-3) / 1e12, "timing": "cuda graph replay"}
+        ref = legs.get("reference_gpu", {})
+        if other == "int4" and "ms_per_step" in ref:
+            secondary["speedup_vs_reference_gpu_kernels"] = ref["ms_per_step"] / ms2
 
-    line = None
     if rank == 0:
         cpu = None
         if not args.skip_cpu and world == 1:   # the CPU baseline is an N=1 figure (rank 0's host cores)
@@ -587,24 +697,17 @@ def main() -> int:
                 cpu = {"value": cpu_v, "unit": "images/s", "cores": cs.cores, "kind": "port", "sample": cs.describe(args.precision, dt, reps)}
             except Exception as e:  # the GPU numbers above must still be reported
                 print(f"[bench] CPU baseline leg failed: {e!r}", file=sys.stderr)
-                cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
-        line = {
-            "metric": METRIC, "value": images_per_s, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int4" if args.precision == "int4" else "nvfp4", "data": "synthetic",
-            "config": workload_config(args),
-            "tflops": world * (f_main + f_lr) / (ms_per_step * 1e-3) / 1e12,
-            "timing": timing_mode,
-            "clocks": clocks.summary(),
+                cpu = {"value": None, "unit": "images/s", "cores": host_threads(), "kind": "port", "sample": f"failed: {e!r}"}
+        _emit({
+            "metric": METRIC, "value": images_per_s, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int4" if args.precision == "int4" else "nvfp4", "data": "synthetic", "config": workload_config(args),
+            "tflops": world * (f_main + f_lr) / (ms_per_step * 1e-3) / 1e12, "timing": timing_mode, "clocks": clk,
             "e2e": {"value": e2e_images, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": ("CUDA graph of the per-layer SVDQW4A4 op calls (quantize + gemm)" if timing_mode.startswith("cuda graph") else "SVDQW4A4 ops launched from Python per layer")
-                            + "; pinned host in/out every step, copies on a second stream (double-buffered staging)"},
-            "gpu_launches": args.steps * launches_per_step,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "secondary": secondary,
-        }
-        _emit(line)
+                    "path": ("CUDA graph of the per-layer module calls" if timing_mode.startswith("cuda graph") else "module calls launched from Python per layer")
+                            + " (SVDQW4A4Linear.forward / forward_qkv / forward_mlp, glue.layernorm / add); pinned host in/out every step, copies on a second stream"},
+            "gpu_launches": args.steps * launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, **legs,
+        })
     replica.shutdown()
     return 0
 

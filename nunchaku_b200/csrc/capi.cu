@@ -1,6 +1,8 @@
 // C-ABI glue shared by all translation units: error string, launch counter, device check.
 #include <cuda.h>
 
+#include <cstdlib>
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
@@ -20,6 +22,43 @@ int fail(int code, const std::string &msg) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+int set_max_smem_once(const void *kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;
+    int dev = 0;
+    NB200_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find({kernel, dev});
+    if (it != done.end() && it->second >= bytes) return NB200_OK;
+    NB200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    done[{kernel, dev}] = bytes;
+    return NB200_OK;
+}
+
+int current_device_sms(int *num_sms) {
+    static std::mutex mu;
+    static std::map<int, int> sms;
+    int dev = 0;
+    NB200_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = sms.find(dev);
+    if (it == sms.end()) {
+        int n = 0;
+        NB200_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        it = sms.emplace(dev, n).first;
+    }
+    *num_sms = it->second;
+    return NB200_OK;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("NB200_PDL");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
 void reset_launch_count() { g_launches = 0; }
 
 // ---- TMA tensor maps (driver entry point resolved through the runtime: no -lcuda) ------------------

@@ -23,6 +23,42 @@ void reset_launch_count();
 int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t inner, uint64_t rows,
                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, and one process may
+// drive several GPUs (ops run with the device of their tensors current).  Returns a status code.
+int set_max_smem_once(const void *kernel, size_t bytes);
+// SM count of the current device (cached per device)
+int current_device_sms(int *num_sms);
+// NB200_PDL=0 disables programmatic dependent launch (default on)
+bool pdl_enabled();
+
+// launch configuration with the optional cluster dimension and the programmatic-dependent-launch attribute
+struct LaunchCfg {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    LaunchCfg(dim3 grid, dim3 block, size_t smem, cudaStream_t stream, unsigned cluster_x = 1) {
+        cfg = cudaLaunchConfig_t{};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        unsigned n = 0;
+        if (cluster_x > 1) {
+            attr[n].id = cudaLaunchAttributeClusterDimension;
+            attr[n].val.clusterDim.x = cluster_x;
+            attr[n].val.clusterDim.y = 1;
+            attr[n].val.clusterDim.z = 1;
+            n++;
+        }
+        if (pdl_enabled()) {
+            attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[n].val.programmaticStreamSerializationAllowed = 1;
+            n++;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = n;
+    }
+};
+
 #define NB200_CUDA_CHECK(expr)                                                                      \
     do {                                                                                            \
         cudaError_t _e = (expr);                                                                    \

@@ -27,6 +27,7 @@
 namespace nb200 {
 
 int gemm_w4a4_2cta_dispatch(const nb200_gemm_args &a, cudaStream_t stream);
+int gemm_nvfp4_cluster_dispatch(const nb200_gemm_args &a, cudaStream_t stream, int pairs);
 
 namespace {
 
@@ -278,6 +279,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
     tc_fence_after_sync();
     const uint32_t tmem_base = s.tmem_base;
     const long long t_setup = clock64() - t_kernel0;
+    griddep_launch_dependents();   // the next kernel in the stream may start its own setup on SMs this grid leaves idle
+    griddep_wait();                // ... and this one touches global memory only after its predecessor has completed
 
     // INT4: 1024 threads start with 64 registers each; every warp group (4 warps) re-sizes its share as the first
     // instruction of its role: producer/MMA/alloc group 56, epilogue group 128, the six converter groups 48.
@@ -1014,22 +1017,15 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.attn_tokens = a.attn_tokens;
     for (int i = 0; i < NB200_MAX_LORA_SCALES; i++) p.lora_scales[i] = a.lora_scales[i];
 
-    static int num_sms_cached = 0;
-    if (num_sms_cached == 0) {
-        int dev = 0;
-        NB200_CUDA_CHECK(cudaGetDevice(&dev));
-        NB200_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_cached, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int num_sms = a.num_sms > 0 ? a.num_sms : num_sms_cached;
+    int num_sms_dev = 0;
+    if (int rc2 = current_device_sms(&num_sms_dev)) return rc2;
+    const int num_sms = a.num_sms > 0 ? a.num_sms : num_sms_dev;
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     const size_t smem_bytes = sizeof(S) + 1024;
     auto kern = gemm_w4a4_kernel<FP4, hT, BN, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        NB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-        attr_set = true;
-    }
-    kern<<<grid, C::kThreads, smem_bytes, stream>>>(tm_act, tm_wgt, tm_out, tm_ld, p);
+    if (int rc2 = set_max_smem_once(reinterpret_cast<const void *>(kern), smem_bytes)) return rc2;
+    LaunchCfg lc(dim3(grid), dim3(C::kThreads), smem_bytes, stream);
+    NB200_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tm_act, tm_wgt, tm_out, tm_ld, p));
     count_launch();
     NB200_CUDA_CHECK(cudaGetLastError());
     return NB200_OK;
@@ -1045,6 +1041,16 @@ int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
                 return launch<FP4, hT, 256, EPI_QUANT>(a, stream);
         }
         return launch<FP4, hT, 128, EPI_QUANT>(a, stream);
+    }
+    // NVFP4 on clusters (gemm_nvfp4_cluster.cu): 256x256 pair tiles, two pairs per cluster sharing A by TMA multicast.
+    // block_n = 1024 / 2048 force one / two pairs per cluster; auto picks it whenever there are enough pair tiles to
+    // fill the chip (the 256-token text stream keeps the narrow single-CTA tiles: more CTAs busy).
+    if constexpr (FP4) {
+        if (a.block_n == 1024 || a.block_n == 2048) return gemm_nvfp4_cluster_dispatch(a, stream, a.block_n / 1024);
+        // measured on one box (tools/gemm_ablate.py, profiles/r02_ablation.md): one pair per cluster == the r01 pair kernel on the plain
+        // epilogue and it carries the RoPE epilogue on 256-wide tiles; two pairs per cluster (A multicast) is NOT faster -- the bound
+        // is what each SM has to receive, which multicast does not change -- and only 33 clusters of 4 fit on the 148 SMs
+        if (a.block_n == 0 && a.N % 256 == 0 && (a.Mp / 256) * (a.N / 256) >= 64) return gemm_nvfp4_cluster_dispatch(a, stream, 1);
     }
     if (a.rotary_emb != nullptr) return launch<FP4, hT, 128, EPI_ROPE>(a, stream);
     if (a.block_n == 512) {  // CTA pairs (cta_group::2), 256 x 256 tiles

@@ -226,6 +226,8 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
     tc_fence_after_sync();
     const uint32_t tmem_base = s.tmem_base;
     const long long t_setup = clock64() - t_kernel0;
+    griddep_launch_dependents();
+    griddep_wait();
 
     if (warp == 0) {
         // =================================== TMA producer (both CTAs) ===============================
@@ -605,34 +607,15 @@ int launch2(const nb200_gemm_args &a, cudaStream_t stream) {
     p.debug = dbg;
     for (int i = 0; i < NB200_MAX_LORA_SCALES; i++) p.lora_scales[i] = a.lora_scales[i];
 
-    static int num_sms_cached = 0;
-    if (num_sms_cached == 0) {
-        int dev = 0;
-        NB200_CUDA_CHECK(cudaGetDevice(&dev));
-        NB200_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_cached, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int num_sms = a.num_sms > 0 ? a.num_sms : num_sms_cached;
+    int num_sms_dev = 0;
+    if (int rc2 = current_device_sms(&num_sms_dev)) return rc2;
+    const int num_sms = a.num_sms > 0 ? a.num_sms : num_sms_dev;
     const int pairs = p.num_tiles < num_sms / 2 ? p.num_tiles : num_sms / 2;
     const size_t smem_bytes = sizeof(S) + 1024;
     auto kern = gemm_w4a4_2cta_kernel<FP4, hT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        NB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-        attr_set = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(C::kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    NB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm_act, tm_wgt, tm_out, tm_sfa, tm_sfb, tm_lu, p));
+    if (int rc2 = set_max_smem_once(reinterpret_cast<const void *>(kern), smem_bytes)) return rc2;
+    LaunchCfg lc(dim3(2 * pairs), dim3(C::kThreads), smem_bytes, stream, 2);
+    NB200_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tm_act, tm_wgt, tm_out, tm_sfa, tm_sfb, tm_lu, p));
     count_launch();
     return NB200_OK;
 }

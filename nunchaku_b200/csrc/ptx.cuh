@@ -88,6 +88,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 #endif
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still running; `griddep_wait` blocks until the predecessor has completed and its writes are
+// visible (no-ops for ordinary launches).  Every kernel here does its setup (barrier init, TMEM allocation, tensor-map
+// prefetch), then launch_dependents + wait, then touches global memory.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // generic-proxy writes -> visible to the async proxy (TMA store / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -271,6 +278,16 @@ __device__ __forceinline__ void tma_load_2d_cg2(void *smem_dst, const void *tmap
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// The same, multicast: the box lands at the same CTA-relative offset in every CTA of `mask`, and each destination CTA credits
+// the bytes to the mbarrier at this offset in the LEADER of its own pair (peer bit cleared), as CUTLASS's
+// SM100_TMA_2SM_LOAD_MULTICAST does.
+__device__ __forceinline__ void tma_load_2d_cg2_mc(void *smem_dst, const void *tmap, uint64_t *bar, int32_t c0, int32_t c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1)
         : "memory");
 }
 

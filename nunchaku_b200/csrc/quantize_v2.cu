@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
         fence_mbar_init();
     }
     __syncthreads();
+    griddep_launch_dependents();
+    griddep_wait();   // x is the previous kernel's output
 
     if (warp == kConsumers) {
         // ============================ TMA producer ==============================================
@@ -478,7 +480,7 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
         ks = (160 + row_blocks - 1) / row_blocks;
         if (ks > G / 4) ks = G / 4;   // at least 4 groups (256 k) per CTA
         if (ks < 1) ks = 1;
-        const size_t need = static_cast<size_t>(ks) * a.Mp * 32 * sizeof(float) + static_cast<size_t>(row_blocks) * sizeof(unsigned int);
+        const size_t need = static_cast<size_t>(ks) * a.Mp * 32 * sizeof(float) + ((static_cast<size_t>(row_blocks) * sizeof(unsigned int) + 255) & ~static_cast<size_t>(255));
         if (need > static_cast<size_t>(a.workspace_bytes)) ks = 1;
     }
     p.KS = ks;
@@ -486,12 +488,9 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
     p.ws_partial = a.workspace ? reinterpret_cast<float *>(static_cast<uint8_t *>(a.workspace) + ((static_cast<size_t>(row_blocks) * 4 + 255) & ~static_cast<size_t>(255))) : nullptr;
     const size_t smem = sizeof(Q2Smem) + 1024;
     auto kern = quantize_v2_kernel<hT, FP4>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        NB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
-    }
-    kern<<<dim3(row_blocks, ks), kThreads, smem, stream>>>(tm_x, p);
+    if (int rc2 = set_max_smem_once(reinterpret_cast<const void *>(kern), smem)) return rc2;
+    LaunchCfg lc(dim3(row_blocks, ks), dim3(kThreads), smem, stream);
+    NB200_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tm_x, p));
     count_launch();
     NB200_CUDA_CHECK(cudaGetLastError());
     return NB200_OK;

@@ -61,3 +61,39 @@ def on_device_of(arg_name: str, position: int = 0):
         return wrapper
 
     return deco
+
+
+def pack_rotemb(sin: torch.Tensor, cos: torch.Tensor) -> torch.Tensor:
+    """Rotary table in the layout the RMSNorm+RoPE epilogue reads (the reference's ``pack_rotemb``,
+    nunchaku/models/transformers/transformer_flux.py:60-92; consumer epilogues.cuh:283-300): ``sin`` / ``cos`` are [M, 64] fp32,
+    pair i rotating head columns (2i, 2i+1); M a multiple of 16.  Returns fp32 [M, 128].
+
+    The packed order is the fp32 accumulator-fragment order of a 16-row tile: [M/16][pair/4][row%8][pair%4][(row%16)/8][sin|cos],
+    which is a pure axis permutation of the logical [M/16][(row%16)/8][row%8][pair/4][pair%4][sin|cos]."""
+    M, P = sin.shape
+    if P != 64 or M % 16 != 0 or cos.shape != sin.shape:
+        raise ValueError("pack_rotemb: sin / cos must be [M, 64] with M a multiple of 16")
+    t = torch.stack([sin.to(torch.float32), cos.to(torch.float32)], dim=-1)       # [M, 64, 2]
+    t = t.view(M // 16, 2, 8, 16, 4, 2).permute(0, 3, 2, 4, 1, 5)                  # -> [mb, pair/4, row%8, pair%4, hi, s]
+    return t.reshape(M, 128).contiguous()
+
+
+def attach(model) -> int:
+    """Bind-onto-the-reference helper: after the operator functions have been patched onto the
+    reference's modules, install ``load_state_dict`` hooks on every module that owns SVDQuant parameters so that the converted
+    weight copies (``nunchaku_b200.repack`` cache) are dropped whenever a checkpoint / LoRA is loaded in place.  Returns the
+    number of modules hooked."""
+    from . import repack
+
+    names = ("qweight", "wscales", "bias", "smooth_factor", "proj_down", "proj_up", "wcscales")
+    hooked = 0
+    for mod in model.modules():
+        if hasattr(mod, "qweight") and hasattr(mod, "proj_up"):
+            def _drop(module, _keys, _names=names):
+                for n in _names:
+                    p = getattr(module, n, None)
+                    if isinstance(p, torch.Tensor):
+                        repack.invalidate(p)
+            mod.register_load_state_dict_post_hook(_drop)
+            hooked += 1
+    return hooked

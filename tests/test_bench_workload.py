@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_layer_list_matches_flux_schnell():
     layers = bench.layer_list()
     assert len(layers) == 19 * 2 * 4 + 38 * 4 == 304
-    params_per_block = sum(K * N for _, K, N, _ in bench.BLOCK_LINEARS)
+    params_per_block = sum(K * N for _, K, N in bench.BLOCK_LINEARS)
     assert params_per_block == 113_246_208                      # 113.25 M 4-bit parameters per block
     f_main, f_lr = bench.step_flops()
     tokens = bench.IMG_TOKENS + bench.TXT_TOKENS
@@ -22,7 +22,7 @@ def test_layer_list_matches_flux_schnell():
     assert abs(f_main / 1e12 - 56.2) < 0.1                      # SURVEY: 56.2 TFLOP / step
     assert abs(f_main * bench.STEPS_PER_IMAGE / 1e12 - 225) < 1  # 225 TFLOP / image
     assert f_lr < 0.03 * f_main                                 # low-rank branch ~2 % of the FLOPs at r = 32
-    shapes = {(M, K, N) for _, M, K, N, _ in layers}
+    shapes = {(M, K, N) for _, M, K, N in layers}
     assert (4096, 3072, 3072) in shapes and (4352, 3072, 12288) in shapes and (256, 12288, 3072) in shapes
 
 

@@ -328,3 +328,48 @@ def test_fused_gelu_mlp_both_routes_agree(precision):
         finally:
             FU.FUSE_FC1_EPILOGUE = None
     assert (ys[True] - ys[False]).norm() <= 2e-3 * ys[True].norm()
+
+
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("block_n,H", [(1024, 2), (2048, 4), (1024, 3)])
+def test_qkv_rmsnorm_rope_cluster_kernel(hT, block_n, H):
+    """NVFP4 cluster kernel's RMSNorm + RoPE epilogue (one 128-wide head per epilogue group; H = 3: a 256-wide tile straddles
+    the Q/K boundary) and its PackQKV variant, against the oracle and against its own row-major result."""
+    from nunchaku_b200.ops import gemm as G
+    from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
+
+    if (3 * H * 128) % (256 * (block_n // 1024)) != 0:
+        pytest.skip("N must be a multiple of the cluster tile width")
+    K, R, M = 256, 32, 300
+    N = 3 * H * 128
+    layer = O.make_synthetic_layer(N, K, R, fp4=True, hT=hT, seed=271)
+    g = torch.Generator().manual_seed(272)
+    norm_q = (1.0 + 0.2 * torch.randn(128, generator=g)).to(hT)
+    norm_k = (1.0 + 0.2 * torch.randn(128, generator=g)).to(hT)
+    x = O.make_activations(M, K, hT, seed=273, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=True)
+    Mp = qa.q.shape[0]
+    ang = torch.rand(Mp, 64, generator=g) * 6.283
+    rsin, rcos = torch.sin(ang), torch.cos(ang)
+    params = ref_layout_params(layer)
+    act, asc = _pack_act(qa, True, hT)
+    common = dict(act=act, wgt=params["qweight"], ascales=asc, wscales=params["wscales"], lora_act_in=qa.lora_act.cuda(),
+                  lora_up=params["proj_up"], bias=params["bias"], fp4=True, alpha=layer.alpha, wcscales=params["wcscales"],
+                  norm_q=norm_q.cuda(), norm_k=norm_k.cuda(), rotary_emb=F.pack_rotemb(rsin, rcos).cuda())
+    out = torch.full((Mp, N), float("nan"), dtype=hT, device="cuda")
+    outs = [torch.full((1, H, Mp, 128), 7.0, dtype=torch.float16, device="cuda") for _ in range(3)]
+    G.BLOCK_N_OVERRIDE = block_n
+    try:
+        svdq_gemm_w4a4_cuda(out=out, **common)
+        svdq_gemm_w4a4_cuda(out_q=outs[0], out_k=outs[1], out_v=outs[2], attn_tokens=M, **common)
+        torch.cuda.synchronize()
+    finally:
+        G.BLOCK_N_OVERRIDE = 0
+    kw = dict(qa=qa.q, ascales=qa.scales, qw=layer.qw, wscales=layer.wscales, hT=hT, M=M, bias=layer.bias, lora_act=qa.lora_act,
+              lora_up=layer.lora_up, fp4=True, alpha=layer.alpha, wcscales=layer.wcscales, rope=(norm_q, norm_k, rsin, rcos))
+    _assert_parity(out[:M], O.gemm_w4a4(mode="exact", **kw).out, O.gemm_w4a4(mode="ref", **kw).out, hT, f"cluster rope bn={block_n} H={H} {hT}")
+    want = out.float().to(torch.float16).view(Mp, 3, H, 128).permute(1, 2, 0, 3).cpu()
+    for part in range(3):
+        got = outs[part][0].cpu()
+        assert torch.equal(got[:, :M].view(torch.int16), want[part][:, :M].view(torch.int16)), f"part {part}"
+        assert torch.isnan(got[:, M:]).all() if part == 1 else bool((got[:, M:] == 0).all())

@@ -82,10 +82,12 @@ def _assert_parity(out, y_exact, y_ref, hT, name):
     assert e_exact <= ref_noise + tol_exact, msg
 
 
-@pytest.mark.parametrize("block_n", [128, 256, 512])   # 512 = CTA-pair kernel (cta_group::2)
+@pytest.mark.parametrize("block_n", [128, 256, 512, 1024])   # 512 = CTA-pair kernel (cta_group::2), 1024 = NVFP4 cluster kernel (one pair)
 @pytest.mark.parametrize("fp4", [False, True])
 @pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
 def test_gemm_small(fp4, hT, block_n):
+    if block_n >= 1024 and not fp4:
+        pytest.skip("the cluster kernel is NVFP4 only")
     N, K, R, M = 256, 384, 32, 200       # K not a multiple of 256: exercises the FP4 k tail
     layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=11)
     x = O.make_activations(M, K, hT, seed=12, smooth=layer.smooth)
@@ -247,3 +249,34 @@ def test_gemm_cta_pair_many_tiles_and_k_tail(fp4):
     finally:
         G.NUM_SMS_OVERRIDE = 0
     _assert_parity(out, _oracle(layer, qa, M, "exact"), _oracle(layer, qa, M, "ref"), hT, f"cta-pair many tiles fp4={fp4}")
+
+
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("block_n", [1024, 2048])   # NVFP4 cluster kernel: one / two CTA pairs per cluster (A multicast)
+def test_gemm_cluster_kernel_small_k_tail(hT, block_n):
+    N, K, R, M = 512, 384, 32, 200       # K not a multiple of 256: k tail of the 256-element stages; ragged M
+    layer = O.make_synthetic_layer(N, K, R, fp4=True, hT=hT, seed=211)
+    x = O.make_activations(M, K, hT, seed=212, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=True)
+    out = _gemm(layer, qa, ref_layout_params(layer), M, block_n=block_n)
+    _assert_parity(out, _oracle(layer, qa, M, "exact"), _oracle(layer, qa, M, "ref"), hT, f"cluster small bn={block_n}")
+
+
+@pytest.mark.parametrize("block_n", [1024, 2048])
+@pytest.mark.parametrize("silu", [False, True])
+def test_gemm_cluster_kernel_many_tiles_phase_wrap(block_n, silu):
+    """persistent loop over 8 pair tiles per pair on a 4-SM grid: stage ring, accumulator and low-rank phases wrap"""
+    hT = torch.bfloat16
+    N, K, R, M = 1024, 640, 48, 900
+    layer = O.make_synthetic_layer(N, K, R, fp4=True, hT=hT, seed=221)
+    x = O.make_activations(M, K, hT, seed=222, smooth=layer.smooth)
+    qa = O.quantize_w4a4_act_fuse_lora(x, layer.smooth, layer.lora_down, fp4=True)
+    from nunchaku_b200.ops import gemm as G
+
+    G.NUM_SMS_OVERRIDE = 4
+    try:
+        out = _gemm(layer, qa, ref_layout_params(layer), M, block_n=block_n, fuse_silu=silu, lora_scales=[0.5, 2.0, 1.0])
+    finally:
+        G.NUM_SMS_OVERRIDE = 0
+    kw = dict(lora_scales=[0.5, 2.0, 1.0], act="silu" if silu else "none")
+    _assert_parity(out, _oracle(layer, qa, M, "exact", **kw), _oracle(layer, qa, M, "ref", **kw), hT, f"cluster many tiles bn={block_n} silu={silu}")

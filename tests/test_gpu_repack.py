@@ -62,3 +62,102 @@ def test_lowrank(rp, dtype, R):
     assert torch.allclose(got_up2.float(), exp2.float(), rtol=2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10, atol=0)
     got_dn = rp.lora_down(F.pack_lowrank(ld, down=True).cuda()).cpu()
     assert torch.equal(got_dn, L.lora_down_frags(ld))
+
+
+def _module(layer, precision="int4", act_unsigned=False, device="cuda"):
+    from gpu_util import ref_layout_params
+    from nunchaku_b200.models.linear import SVDQW4A4Linear
+
+    N, K = layer.qw.shape
+    p = ref_layout_params(layer, device=device)
+    m = SVDQW4A4Linear(K, N, rank=layer.lora_up.shape[1], bias=True, precision=precision, act_unsigned=act_unsigned, torch_dtype=layer.hT, device=device)
+    sd = {"qweight": p["qweight"], "wscales": p["wscales"], "bias": p["bias"], "smooth_factor": p["smooth"], "smooth_factor_orig": p["smooth"],
+          "proj_down": p["proj_down"], "proj_up": p["proj_up"]}
+    if layer.fp4:
+        sd["wcscales"] = p["wcscales"]
+        m.wtscale = layer.alpha
+    m.load_state_dict(sd)
+    return m, sd
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+def test_module_owned_weights_follow_reloads_and_release(fp4):
+    """load A -> forward -> load B into the SAME module -> forward must use B (load_state_dict hook drops the converted copy);
+    in-place edits need invalidate(); release_reference_layout() frees the checkpoint-layout tensors and the layer still runs."""
+    from oracle import svdq as O
+
+    hT = torch.bfloat16
+    la = O.make_synthetic_layer(256, 256, 32, fp4=fp4, hT=hT, seed=301)
+    lb = O.make_synthetic_layer(256, 256, 32, fp4=fp4, hT=hT, seed=302)
+    x = O.make_activations(200, 256, hT, seed=303).cuda().view(1, 200, 256)
+    prec = "nvfp4" if fp4 else "int4"
+    ma, _ = _module(la, prec)
+    mb, sdb = _module(lb, prec)
+    ya, yb = ma(x).clone(), mb(x).clone()
+    assert O.rel_fro(ya.cpu(), yb.cpu()) > 0.5
+    if fp4:
+        ma.wtscale = lb.alpha
+    ma.load_state_dict(sdb)
+    assert torch.equal(ma(x), yb)
+    # in-place edit of a parameter: invisible until invalidate()
+    ma.bias.data.add_(1.0)
+    assert torch.equal(ma(x), yb)
+    ma.invalidate()
+    assert O.rel_fro(ma(x).cpu(), (yb.float() + 1.0).cpu()) < 1e-2
+    freed = mb.release_reference_layout()
+    assert freed >= 256 * 128 and mb.qweight.numel() == 0
+    assert torch.equal(mb(x), yb)
+
+
+def test_raw_op_cache_invalidate_after_inplace_update():
+    """the raw-tensor operator path (reference signature) caches converted copies per source tensor: `.data.copy_` does not bump
+    `_version`, so the loader must call repack.invalidate() -- and then gets the new weights"""
+    from nunchaku_b200 import repack
+    from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
+    from nunchaku_b200.ops.quantize import svdq_quantize_w4a4_act_fuse_lora_cuda
+    from gpu_util import ref_layout_params
+    from oracle import svdq as O
+
+    hT = torch.bfloat16
+    la = O.make_synthetic_layer(256, 256, 32, fp4=False, hT=hT, seed=311)
+    lb = O.make_synthetic_layer(256, 256, 32, fp4=False, hT=hT, seed=312)
+    pa, pb = ref_layout_params(la), ref_layout_params(lb)
+    x = O.make_activations(256, 256, hT, seed=313).cuda()
+
+    def run(p):
+        q, s, l = svdq_quantize_w4a4_act_fuse_lora_cuda(x, lora_down=p["proj_down"], smooth=p["smooth"])
+        out = torch.empty(256, 256, dtype=hT, device="cuda")
+        svdq_gemm_w4a4_cuda(act=q, wgt=p["qweight"], out=out, ascales=s, wscales=p["wscales"], lora_act_in=l, lora_up=p["proj_up"], bias=p["bias"])
+        return out
+
+    ya, yb = run(pa), run(pb)
+    for k in ("qweight", "wscales", "bias", "smooth", "proj_down", "proj_up"):
+        pa[k].data.copy_(pb[k])
+    stale = run(pa)
+    assert torch.equal(stale, ya)            # documented behaviour: stale until told
+    for k in ("qweight", "wscales", "bias", "smooth", "proj_down", "proj_up"):
+        repack.invalidate(pa[k])
+    assert torch.equal(run(pa), yb)
+    # a tensor object that moves to new storage evicts its old entries
+    n0 = len(repack._cache)
+    pa["qweight"].data = pb["qweight"].clone()
+    run(pa)
+    assert len(repack._cache) <= n0 + 1
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_layer_on_second_gpu_while_first_is_current():
+    """per-device launch state (max dynamic shared memory attribute, SM count, cluster occupancy): cuda:1 used while cuda:0 is current"""
+    from oracle import svdq as O
+
+    hT = torch.bfloat16
+    for fp4 in (False, True):
+        layer = O.make_synthetic_layer(512, 256, 32, fp4=fp4, hT=hT, seed=321)
+        x = O.make_activations(300, 256, hT, seed=322)
+        m0, _ = _module(layer, "nvfp4" if fp4 else "int4", device="cuda:0")
+        y0 = m0(x.to("cuda:0").view(1, 300, 256))
+        torch.cuda.set_device(0)
+        m1, _ = _module(layer, "nvfp4" if fp4 else "int4", device="cuda:1")
+        y1 = m1(x.to("cuda:1").view(1, 300, 256))
+        torch.cuda.synchronize("cuda:1")
+        assert torch.equal(y0.cpu(), y1.cpu())

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--M", type=int, default=4096)
     ap.add_argument("--K", type=int, default=3072)
     ap.add_argument("--N", type=int, default=3072)
-    ap.add_argument("--bn", default="0,512")
+    ap.add_argument("--bn", default="256,512,1024,2048")
     ap.add_argument("--fused", action="store_true", help="profile the fc1 -> GELU -> quantise-for-fc2 epilogue (EPI_QUANT)")
     args = ap.parse_args()
     from nunchaku_b200.ops import gemm as G
@@ -67,7 +67,7 @@ def main():
             G.BLOCK_N_OVERRIDE = 0
             us = e0.elapsed_time(e1) * 1e3
             pr = prof.cpu().double()
-            used = pr[:, 10] > 0 if bn != 512 else pr[:, 5] > 0
+            used = pr[:, 10] > 0 if bn < 512 else pr[:, 5] > 0
             print(f"== {prec} M={args.M} K={args.K} N={args.N} bn={bn}: {us:.1f} us  ({2*args.M*args.K*args.N/us/1e6:.0f} TFLOP/s)  CTAs with data {int(used.sum())}")
             for k, name in SLOTS.items():
                 col = pr[:, k]

@@ -61,7 +61,7 @@ def main():
     ap.add_argument("--iters", type=int, default=15)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.json"))
     ap.add_argument("--shapes", default="flux")
-    ap.add_argument("--bn", default="0,128,256,512")
+    ap.add_argument("--bn", default="0,256,512,1024,2048")
     args = ap.parse_args()
     from nunchaku_b200.ops import gemm as G
 
