@@ -104,9 +104,9 @@ static_assert(sizeof(SmemC) + 1024 <= 232448, "shared memory budget (227 KB per 
     } while (0)
 
 struct PipeState {
-    uint32_t idx = 0, phase = 0;
+    uint32_t idx = 0, phase = 0, n = kStages;
     __device__ __forceinline__ void advance() {
-        if (++idx == kStages) {
+        if (++idx == n) {
             idx = 0;
             phase ^= 1;
         }
@@ -164,6 +164,7 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
     // Tried and dropped (r02, tools/gemm_ablate.py on one box): scale factors on their own mbarrier, loaded first and copied to TMEM one
     // stage ahead -- 12 % SLOWER on 4096x3072x3072, 26 % slower on K = 12288 (34.8 -> 39.0 us, 86 -> 108 us)
     const int lora_chunks = (p.has_lora && !(p.debug & 128)) ? p.Rp / kLoraChunk : 0;
+    const uint32_t ring = (p.debug & 2048) ? 2 : ((p.debug & 1024) ? 3 : kStages);   // ablation: shallower TMA ring (results stay valid)
     constexpr uint16_t kMaskAll = (1u << kCtas) - 1;
     const uint16_t mask_pair = static_cast<uint16_t>(3u << (2 * pi));
     const uint16_t mask_a = static_cast<uint16_t>(kPairs == 2 ? ((1u << q) | (1u << (q + 2))) : (1u << q));
@@ -201,6 +202,7 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
         // =================================== TMA producer (every CTA) ================================
         if (elect_one()) {
             PipeState st;
+            st.n = ring;
             uint32_t lora_phase = 0;
             long long t_empty = 0;
             for (int ct = cluster_id; ct < p.num_ct; ct += num_clusters) {
@@ -222,8 +224,15 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                         tma_load_2d_cg2(s.sa[st.idx], &tm_sfa, &s.full[st.idx], 0, sfa_row + 4 * kb);
                     }
                     tma_load_2d_cg2(s.b[st.idx], &tm_wgt, &s.full[st.idx], kb * 128, nh);
-                    // weight scale factors of columns [n0 + 128 q, +128): both CTAs of the pair need them
-                    tma_load_2d_cg2_mc(s.sb[st.idx] + q * (kSbBytes / 2), &tm_sfb, &s.full[st.idx], 0, sfb_row + 4 * kb, mask_pair);
+                    if constexpr (kPairs == 2) {
+                        // weight scale factors of columns [n0 + 128 q, +128), multicast to both CTAs of the pair
+                        tma_load_2d_cg2_mc(s.sb[st.idx] + q * (kSbBytes / 2), &tm_sfb, &s.full[st.idx], 0, sfb_row + 4 * kb, mask_pair);
+                    } else {
+                        // one pair per cluster: each CTA fetches the scale factors of all 256 columns itself -- measured ~4 % faster than
+                        // splitting them and multicasting inside the pair (tools/gemm_ablate.py, r02)
+                        tma_load_2d_cg2(s.sb[st.idx], &tm_sfb, &s.full[st.idx], 0, (n0 / 128) * k64_total + 4 * kb);
+                        tma_load_2d_cg2(s.sb[st.idx] + kSbBytes / 2, &tm_sfb, &s.full[st.idx], 0, (n0 / 128 + 1) * k64_total + 4 * kb);
+                    }
                     st.advance();
                 }
                 for (int c = 0; c < lora_chunks; c++) {
@@ -240,6 +249,7 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
         // ==================================== MMA issuer (pair leaders) ===============================
         if (leader && elect_one()) {
             PipeState st;
+            st.n = ring;
             uint32_t lora_phase = 0, acc_phase = 0;
             long long t_tmem_empty = 0, t_full = 0, t_lora = 0, t_first = 0;
             const long long t_mma0 = clock64();

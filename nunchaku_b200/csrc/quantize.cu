@@ -298,7 +298,10 @@ int quantize_v2_dispatch(const nb200_quantize_args &a, cudaStream_t stream);
 extern "C" __attribute__((visibility("default"))) long long nb200_quantize_workspace_bytes(int Mp, int K) {
     if (Mp <= 0 || K <= 0) return 0;
     const long long row_blocks = Mp / 32;
-    const long long ks_max = (160 + row_blocks - 1) / row_blocks;
+    // K split so that the row blocks x splits fill 2 CTA slots on each of up to 160 SMs, never finer than 256 k per split (quantize_v2.cu)
+    long long ks_max = (2 * 160 + row_blocks - 1) / row_blocks;
+    if (ks_max > K / 256) ks_max = K / 256;
+    if (ks_max < 1) ks_max = 1;
     return ((row_blocks * 4 + 255) / 256) * 256 + ks_max * Mp * 32 * 4;
 }
 
@@ -306,11 +309,13 @@ extern "C" __attribute__((visibility("default"))) int nb200_quantize_w4a4_act_fu
     using namespace nb200;
     reset_launch_count();
     NB200_REQUIRE(a != nullptr, "args is NULL");
-    NB200_REQUIRE(a->input && a->output && a->oscales && a->lora_down && a->lora_act_out, "NULL tensor");
+    NB200_REQUIRE(a->input && a->output && a->oscales, "NULL tensor");
+    NB200_REQUIRE(a->R == 0 || (a->lora_down && a->lora_act_out), "lora_down and lora_act_out are required when rank > 0");
     NB200_REQUIRE(a->M > 0 && a->M <= a->Mp, "M must be in (0, Mp]");
     NB200_REQUIRE(a->Mp % 256 == 0, "Mp must be a multiple of 256 (pad_size)");
     NB200_REQUIRE(a->K % 128 == 0 && a->K > 0, "K must be a positive multiple of 128");
-    NB200_REQUIRE(a->R % 16 == 0 && a->R > 0, "rank must be a positive multiple of 16");
+    NB200_REQUIRE(a->R % 16 == 0 && a->R >= 0, "rank must be a multiple of 16 (0: quantise only, as the reference's rank-0 GEMM_W4A4)");
+    NB200_REQUIRE(a->R > 0 || !a->fuse_glu, "rank 0 is not supported together with fuse_glu");
     NB200_REQUIRE(a->dtype == NB200_FP16 || a->dtype == NB200_BF16, "dtype must be fp16 or bf16");
     NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->input) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->output) & 15) == 0,
                   "input/output must be 16-byte aligned");

@@ -24,10 +24,13 @@ namespace {
 using namespace ptx;
 
 constexpr int kRows = 32;
-constexpr int kConsumers = 16;   // 4 warps per scheduler: the kernel is issue/latency bound, not bandwidth bound
-constexpr int kStages = 32;      // two tiles in flight per consumer warp (128 KB of TMA traffic outstanding)
-constexpr int kThreads = (kConsumers + 1) * 32;
 constexpr int kTileBytes = kRows * 128;
+// Two shapes of the same kernel (template parameters kConsumers consumer warps, kStages ring slots of 4 KB):
+//   <16, 32>  one CTA per SM (default): 200 KB of shared memory, 128 KB of TMA traffic in flight per SM
+//   < 8, 16>  TWO CTAs per SM + K split (NB200_QUANT_CFG=1): 2 x 148 CTA slots, 128 row blocks x 2 K halves for the 4096-row
+//             activations instead of 128 CTAs on 148 SMs.  Measured SLOWER on B200 (r02, tools/op_sweep.py on one box: 26.7 vs
+//             22.5 us at M=4096 K=3072, 62.5 vs 55-59 us at K=12288): the split's workspace round trip + ticket + last-CTA
+//             reduction cost more than the idle 20 SMs; kept as an ablation switch
 
 struct Q2Params {
     uint8_t *q;
@@ -42,6 +45,7 @@ struct Q2Params {
     int unsigned_shift;   // INT4: quantise (x + 0.171875) / smooth to unsigned codes (scale = max / 15)
 };
 
+template <int kConsumers, int kStages>
 struct alignas(1024) Q2Smem {
     alignas(1024) uint8_t tile[kStages][kTileBytes];
     float red[kConsumers][kRows][33];
@@ -89,10 +93,12 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint32_t (&w)[4]) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
 
-template <typename hT, bool FP4>
-__global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
+template <typename hT, bool FP4, int kConsumers, int kStages>
+__global__ void __launch_bounds__((kConsumers + 1) * 32, kConsumers == 8 ? 2 : 1)
+quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
     using Tr = HalfTraits<hT>;
     using T2 = typename Tr::T2;
+    using Q2Smem = nb200::Q2Smem<kConsumers, kStages>;
     extern __shared__ uint8_t smem_raw[];
     // align inside the SHARED address space (pointer arithmetic on the __shared__ array): a round trip through uintptr_t
     // makes every access to `s` a generic LD/ST instead of LDS/STS (seen in the ncu source view)
@@ -107,8 +113,9 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
     const int g_begin = static_cast<int>((static_cast<long long>(G) * ks) / p.KS);
     const int g_end = static_cast<int>((static_cast<long long>(G) * (ks + 1)) / p.KS);
     const int n_groups = g_end - g_begin;
-    const int n_chunks = p.Rp >> 5;
+    const int n_chunks = p.Rp > 0 ? p.Rp >> 5 : 1;   // rank 0: one pass, quantise only
     const int nt_total = p.Rp >> 3;
+    const bool has_lora = p.Rp > 0;
 
     if (threadIdx.x == 0) {
         prefetch_tensormap(&tm_x);
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                 uint4 bw[4];   // B fragments of the first 32-wide half; the second half is fetched after it is consumed
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    bw[j] = ldg_v4(ldw + (static_cast<size_t>(g * 2) * nt_total + chunk * 4 + j) * 32 + lane);
+                    bw[j] = has_lora ? ldg_v4(ldw + (static_cast<size_t>(g * 2) * nt_total + chunk * 4 + j) * 32 + lane) : make_uint4(0, 0, 0, 0);
                 // x / smooth as the reference's __fdividef computes it (gemm_utils.cuh:329-344): SASS is
                 // "if |b| < 2^-126 scale a and b by 2^24; MUFU.RCP(b) * a".  The reciprocal and the scale depend
                 // only on the column, so they are hoisted out of the 8 row passes of the tile.
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
 
                 // ---- x @ lora_down^T on the un-smoothed tile (lora.cuh:243-353) ---------------------
 #pragma unroll
-                for (int kb = 0; kb < ((p.debug & 1) ? 0 : 2); kb++) {
+                for (int kb = 0; kb < (((p.debug & 1) || !has_lora) ? 0 : 2); kb++) {
 #pragma unroll
                     for (int m = 0; m < 2; m++) {
 #pragma unroll
@@ -390,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
                 if (lane == 0) mbar_arrive(&s.empty[st]);
             }
 
+            if (!has_lora) continue;   // (uniform across the CTA)
             // ---- fixed-order reduction of the per-warp partial projections --------------------------
 #pragma unroll
             for (int m = 0; m < 2; m++)
@@ -452,8 +460,9 @@ __global__ void __launch_bounds__(kThreads, 1) quantize_v2_kernel(const __grid_c
 
 }  // namespace
 
-template <typename hT, bool FP4>
+template <typename hT, bool FP4, int kConsumers, int kStages>
 static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
+    constexpr int kThreads = (kConsumers + 1) * 32;
     CUtensorMap tm_x;
     const CUtensorMapDataType dt = HalfTraits<hT>::kIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     int rc = make_map_2d(&tm_x, dt, a.input, a.K, a.M, static_cast<uint64_t>(a.K) * 2, 64, kRows, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -472,12 +481,15 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
     p.unsigned_shift = a.act_unsigned_shift;
     static const int dbg = getenv("NB200_QUANT_DEBUG") ? atoi(getenv("NB200_QUANT_DEBUG")) : 0;
     p.debug = dbg;
-    // split K across CTAs only when the row blocks alone would leave most SMs idle
+    // split K across CTAs whenever the row blocks alone would not fill every CTA slot of the chip
     const int row_blocks = a.Mp / kRows;
     const int G = a.K / 64;
+    int num_sms = 0;
+    if (int rc2 = current_device_sms(&num_sms)) return rc2;
+    const int slots = num_sms * (kConsumers == 8 ? 2 : 1);
     int ks = 1;
-    if (a.workspace != nullptr && row_blocks < 96 && p.Rp == 32) {
-        ks = (160 + row_blocks - 1) / row_blocks;
+    if (a.workspace != nullptr && row_blocks < (kConsumers == 8 ? slots : 96) && p.Rp == 32) {
+        ks = kConsumers == 8 ? slots / row_blocks : (160 + row_blocks - 1) / row_blocks;   // one wave of CTAs
         if (ks > G / 4) ks = G / 4;   // at least 4 groups (256 k) per CTA
         if (ks < 1) ks = 1;
         const size_t need = static_cast<size_t>(ks) * a.Mp * 32 * sizeof(float) + ((static_cast<size_t>(row_blocks) * sizeof(unsigned int) + 255) & ~static_cast<size_t>(255));
@@ -486,8 +498,8 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
     p.KS = ks;
     p.ws_ticket = static_cast<unsigned int *>(a.workspace);
     p.ws_partial = a.workspace ? reinterpret_cast<float *>(static_cast<uint8_t *>(a.workspace) + ((static_cast<size_t>(row_blocks) * 4 + 255) & ~static_cast<size_t>(255))) : nullptr;
-    const size_t smem = sizeof(Q2Smem) + 1024;
-    auto kern = quantize_v2_kernel<hT, FP4>;
+    const size_t smem = sizeof(Q2Smem<kConsumers, kStages>) + 1024;
+    auto kern = quantize_v2_kernel<hT, FP4, kConsumers, kStages>;
     if (int rc2 = set_max_smem_once(reinterpret_cast<const void *>(kern), smem)) return rc2;
     LaunchCfg lc(dim3(row_blocks, ks), dim3(kThreads), smem, stream);
     NB200_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tm_x, p));
@@ -498,8 +510,13 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
 
 int quantize_v2_dispatch(const nb200_quantize_args &a, cudaStream_t stream) {
     const bool bf16 = a.dtype == NB200_BF16;
-    if (bf16) return a.fp4 ? launch_q2<__nv_bfloat16, true>(a, stream) : launch_q2<__nv_bfloat16, false>(a, stream);
-    return a.fp4 ? launch_q2<__half, true>(a, stream) : launch_q2<__half, false>(a, stream);
+    static const int cfg = getenv("NB200_QUANT_CFG") ? atoi(getenv("NB200_QUANT_CFG")) : 0;   // 0: one CTA per SM (default), 1: two CTAs per SM + K split
+    if (cfg == 0) {
+        if (bf16) return a.fp4 ? launch_q2<__nv_bfloat16, true, 16, 32>(a, stream) : launch_q2<__nv_bfloat16, false, 16, 32>(a, stream);
+        return a.fp4 ? launch_q2<__half, true, 16, 32>(a, stream) : launch_q2<__half, false, 16, 32>(a, stream);
+    }
+    if (bf16) return a.fp4 ? launch_q2<__nv_bfloat16, true, 8, 16>(a, stream) : launch_q2<__nv_bfloat16, false, 8, 16>(a, stream);
+    return a.fp4 ? launch_q2<__half, true, 8, 16>(a, stream) : launch_q2<__half, false, 8, 16>(a, stream);
 }
 
 }  // namespace nb200

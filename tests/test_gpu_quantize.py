@@ -104,3 +104,23 @@ def test_quantize_fuse_glu(fp4):
     deq_ref = O.dequant(ref.q, ref.scales.t().contiguous(), fp4)
     assert O.rel_fro(deq, deq_ref) < 2e-2, diag("glu deq", deq, deq_ref)
     assert O.rel_fro(la.cpu(), ref.lora_act) < 5e-3, diag("glu lora", la, ref.lora_act)
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+def test_quantize_rank_zero(fp4):
+    """the reference's GEMM_W4A4 starts with lora_rank = 0 (src/Linear.cpp:92-117) and only asserts rank % 16 == 0: a rank-0 layer
+    quantises without a low-rank projection.  Codes and scales must equal those of the rank-32 call on the same input."""
+    from nunchaku_b200.ops.quantize import svdq_quantize_w4a4_act_fuse_lora_cuda
+    from oracle import formats as F
+    from oracle import svdq as O
+
+    hT = torch.bfloat16
+    M, K = 300, 512
+    layer = O.make_synthetic_layer(128, K, 32, fp4=fp4, hT=hT, seed=401)
+    x = O.make_activations(M, K, hT, seed=402, smooth=layer.smooth).cuda()
+    smooth = F.pack_channel_vector(layer.smooth).cuda()
+    q32, s32, _ = svdq_quantize_w4a4_act_fuse_lora_cuda(x, lora_down=F.pack_lowrank(layer.lora_down, down=True).cuda(), smooth=smooth, fp4=fp4)
+    q0, s0, la0 = svdq_quantize_w4a4_act_fuse_lora_cuda(x, lora_down=torch.empty(K, 0, dtype=hT, device="cuda"), smooth=smooth, fp4=fp4)
+    torch.cuda.synchronize()
+    assert la0.shape == (512, 0)
+    assert torch.equal(q0[:M], q32[:M]) and torch.equal(s0.view(torch.uint8), s32.view(torch.uint8))

@@ -17,7 +17,7 @@ import torch  # noqa: E402
 
 from op_sweep import make_layer, time_fn  # noqa: E402
 
-CASES = [(0, "full kernel"), (256, "SF copies at stage start (valid)"), (512, "low-rank conversion at tile start (valid)"), (768, "both of the above = r02a kernel (valid)"), (128, "no low-rank"), (16, "no SF copies"), (8, "no epilogue math/stores"), (4, "no MMAs (loads + copies + epilogue)"),
+CASES = [(0, "full kernel"), (1024, "3-stage TMA ring (valid)"), (2048, "2-stage TMA ring (valid)"), (512, "low-rank conversion at tile start (valid)"), (128, "no low-rank"), (16, "no SF copies"), (8, "no epilogue math/stores"), (4, "no MMAs (loads + copies + epilogue)"),
          (96, "no loads, no operand waits (MMA + copies + epilogue)"), (96 + 16, "no loads, no copies (MMA + epilogue)"),
          (96 + 16 + 128, "no loads, no copies, no low-rank"), (96 + 16 + 128 + 8, "MMA issue only"), (4 + 16 + 8 + 128, "load pipeline only")]
 
