@@ -104,3 +104,25 @@ g++ -shared -o "$OUT/libnunchaku_seam.so" "$OBJ/src_Linear.o" "$OBJ/src_Module.o
     -L"$ROOT/nunchaku_b200/_lib" -lnunchaku_b200 -L/usr/local/cuda/lib64 -lcudart -lcublas \
     -Wl,-rpath,/usr/local/cuda/lib64 -Wl,-rpath,'$ORIGIN/../../nunchaku_b200/_lib' -Wl,--no-undefined
 echo "linked $OUT/libnunchaku_seam.so"
+
+# ---- oracle/_ref/pyseam/_C.so: the `nunchaku._C.ops` pybind surface (reference nunchaku/csrc/ops.h + src/interop/torch.cpp, compiled
+# where they lie) on top of the same seam objects.  Needs the torch headers of this interpreter.
+PY="${PYTHON:-python}"
+TORCH_INC=$($PY - <<'PYEOF'
+from torch.utils.cpp_extension import include_paths
+import sysconfig
+print(" ".join("-I" + p for p in include_paths() + [sysconfig.get_paths()["include"]]))
+PYEOF
+)
+TORCH_LIB=$($PY -c "import torch, os; print(os.path.join(os.path.dirname(torch.__file__), 'lib'))")
+PYB_INC=$($PY -c "import pybind11; print(pybind11.get_include())" 2>/dev/null || true)
+mkdir -p "$OUT/pyseam"
+TFLAGS=("${DEFS[@]}" -std=c++20 -O1 -fPIC -w -I /usr/local/cuda/include $TORCH_INC ${PYB_INC:+-I $PYB_INC} -DTORCH_EXTENSION_NAME=_C -D_GLIBCXX_USE_CXX11_ABI=1)
+if [ ! -f "$OBJ/py_torch_interop.o" ] || [ "$REF/src/interop/torch.cpp" -nt "$OBJ/py_torch_interop.o" ]; then
+  g++ "${TFLAGS[@]}" "${INC[@]}" -c "$REF/src/interop/torch.cpp" -o "$OBJ/py_torch_interop.o"
+fi
+g++ "${TFLAGS[@]}" "${INC[@]}" -I "$REF/nunchaku/csrc" -I "$ROOT/include" -c "$SEAM/pybind_ops.cpp" -o "$OBJ/py_pybind_ops.o"
+g++ -shared -o "$OUT/pyseam/_C.so" "$OBJ/py_pybind_ops.o" "$OBJ/py_torch_interop.o" "$OBJ/seam_zgemm_b200.o" "$OBJ/src_kernels_awq_gemv_awq.o" \
+    -L"$ROOT/nunchaku_b200/_lib" -lnunchaku_b200 -L"$TORCH_LIB" -ltorch -ltorch_cpu -ltorch_cuda -lc10 -lc10_cuda -ltorch_python \
+    -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,/usr/local/cuda/lib64 -Wl,-rpath,"$TORCH_LIB" -Wl,-rpath,'$ORIGIN/../../../nunchaku_b200/_lib'
+echo "linked $OUT/pyseam/_C.so"

@@ -1,0 +1,65 @@
+"""The `nunchaku._C.ops` pybind surface on B200 (SURVEY section 8b "Python seam"): oracle/_ref/pyseam/_C.so is the REFERENCE'S OWN
+binding code (nunchaku/csrc/ops.h + src/interop/torch.cpp, compiled where they lie by oracle/ref_build/build_ref.sh) linked on top of
+our definitions of the zgemm.h functions (nunchaku_b200/csrc/seam/zgemm_b200.cpp -> libnunchaku_b200.so).  Route A / Route B
+callers and `QuantizedGEMM` bind exactly here: 29 positional Optional[Tensor] arguments for gemm_w4a4, 8 for the quantizer.
+Checked bit for bit against this package's Python operator layer on the same checkpoint tensors."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+from gpu_util import ref_layout_params
+from oracle import svdq as O
+
+SO = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "pyseam", "_C.so")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(SO), reason="oracle/_ref/pyseam/_C.so not built")]
+
+
+@pytest.fixture(scope="module")
+def C():
+    from nunchaku_b200 import _C as _lib  # noqa: F401  (libnunchaku_b200.so first)
+
+    spec = importlib.util.spec_from_file_location("_C", SO)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+@pytest.mark.parametrize("hT", [torch.bfloat16, torch.float16])
+def test_pybind_ops_match_python_operator_layer(C, fp4, hT):
+    from nunchaku_b200.ops.gemm import svdq_gemm_w4a4_cuda
+    from nunchaku_b200.ops.quantize import svdq_quantize_w4a4_act_fuse_lora_cuda
+
+    N, K, R, M = 512, 384, 32, 300
+    layer = O.make_synthetic_layer(N, K, R, fp4=fp4, hT=hT, seed=501)
+    p = ref_layout_params(layer)
+    x = O.make_activations(M, K, hT, seed=502, smooth=layer.smooth).cuda()
+    Mp = 512
+    # the reference's Python wrappers allocate the outputs and pass everything positionally (nunchaku/ops/quantize.py:68-79, gemm.py:130-160)
+    act = torch.empty(Mp, K // 2, dtype=torch.uint8, device="cuda")
+    asc = torch.empty(K // 16, Mp, dtype=torch.float8_e4m3fn, device="cuda") if fp4 else torch.empty(K // 64, Mp, dtype=hT, device="cuda")
+    la = torch.empty(Mp, R, dtype=torch.float32, device="cuda")
+    C.ops.quantize_w4a4_act_fuse_lora(x, act, asc, p["proj_down"], la, p["smooth"], False, fp4)
+    out = torch.full((M, N), float("nan"), dtype=hT, device="cuda")
+    C.ops.gemm_w4a4(act, p["qweight"], out, None, asc, p["wscales"], None, None, la, p["proj_up"], None, None, None, None, None, p["bias"], None, None,
+                    None, False, [1.0, 1.0], False, fp4, float(layer.alpha), p["wcscales"], None, None, None, 0)
+    q2, s2, la2 = svdq_quantize_w4a4_act_fuse_lora_cuda(x, lora_down=p["proj_down"], smooth=p["smooth"], fp4=fp4)
+    out2 = torch.empty(M, N, dtype=hT, device="cuda")
+    svdq_gemm_w4a4_cuda(act=q2, wgt=p["qweight"], out=out2, ascales=s2, wscales=p["wscales"], lora_act_in=la2, lora_up=p["proj_up"], bias=p["bias"],
+                        fp4=fp4, alpha=layer.alpha, wcscales=p["wcscales"])
+    torch.cuda.synchronize()
+    assert torch.equal(act, q2) and torch.equal(asc.view(torch.uint8), s2.view(torch.uint8)) and torch.equal(la, la2)
+    assert torch.equal(out, out2)
+    y_ref = O.svdq_linear_forward(layer, x.cpu(), mode="ref")
+    assert O.rel_fro(out.cpu(), y_ref) <= 1.5e-2
+
+
+def test_pybind_utils_and_out_of_scope_entries(C):
+    C.utils.set_log_level("info")
+    C.utils.disable_memory_auto_release()
+    C.utils.trim_memory()
+    with pytest.raises(RuntimeError, match="not provided"):
+        t = torch.zeros(1, 1, 256, 128, dtype=torch.float16, device="cuda")
+        C.ops.attention_fp16(t, t, t, torch.zeros(1, 256, 128, dtype=torch.float16, device="cuda"), 1.0)
