@@ -107,7 +107,7 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 r = int(reasons(h))
-                self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "0"] +
+                self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
                                     [("Active" if r & bits[n] else "Not Active") for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
             except Exception:
                 pass
@@ -145,7 +145,9 @@ class ClockSampler:
             for i, n in enumerate(names):
                 if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        pw = sorted(float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit())
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_median": pw[len(pw) // 2] if pw else None, "power_w_max": pw[-1] if pw else None,
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 

@@ -223,6 +223,14 @@ int nb200_litela_vk(int dtype, const void *qkv, void *out_q, float *out_vk, int 
  * Replaces kernels::linearattn_vk_mul_q (gemm_w4a4_launch_impl.cuh:427-448, epilogues.cuh:693-760; eps = 1e-6). */
 int nb200_linearattn_vk_mul_q(int dtype, void *q, const float *vk, int batch, int tokens, int heads, float eps, void *stream);
 
+/* ---- AWQ W4A16 GEMV for the AdaLN modulation linears -----------------------------------------
+ * out[m, n] = sum_k x[m, k] * (code[n, k] * scales[k/64, n] + zeros[k/64, n]),  1 <= M <= 8, group_size == 64.
+ * Replaces gemv_awq (src/kernels/awq/gemv_awq.cu:241-294, GEMV_AWQ::forward src/Linear.cpp:56-86, nunchaku/ops/gemv.py:10-58).
+ * qweight int32 [OC/4, IC/8*4] in the CHECKPOINT layout (read in place, no repack), scales / zeros hT [IC/64, OC], x hT [M, IC],
+ * out hT [M, OC]; the reference's arithmetic (hT dequant FMA, hT product, fp32 accumulation). */
+int nb200_gemv_awq(int dtype, const void *x, const void *qweight, const void *scales, const void *zeros, void *out, int M, int OC, int IC,
+                   int group_size, void *stream);
+
 /* Number of kernels the last nb200_* call on this thread launched (bench bookkeeping). */
 int nb200_last_launch_count(void);
 

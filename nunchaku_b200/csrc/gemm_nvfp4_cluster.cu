@@ -148,6 +148,8 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
     S &s = *reinterpret_cast<S *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
     const long long t_kernel0 = clock64();
+    unsigned long long ns_kernel0 = 0;
+    if (p.prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_kernel0));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -200,7 +202,8 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
 
     if (warp == 0) {
         // =================================== TMA producer (every CTA) ================================
-        if (elect_one()) {
+        // the whole warp runs the loops and polls the barriers (uniform control flow, state in uniform registers); one elected lane issues
+        {
             PipeState st;
             st.n = ring;
             uint32_t lora_phase = 0;
@@ -213,40 +216,133 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                 const int sfa_row = (m0 / 128) * k64_total, sfb_row = (n0 / 128 + q) * k64_total;
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     if (p.debug & 64) break;
-                    NB200_TIMED(t_empty, mbar_wait(&s.empty[st.idx], st.phase ^ 1));
-                    if (leader) mbar_expect_tx(&s.full[st.idx], 2 * kStageBytes);
-                    if constexpr (kPairs == 2) {
-                        // half of the A rows / activation scale blocks, multicast to the CTA with the same q in the other pair
-                        tma_load_2d_cg2_mc(s.a[st.idx] + pi * (kABytes / 2), &tm_act, &s.full[st.idx], kb * 128, m0 + pi * (BM / 2), mask_a);
-                        tma_load_2d_cg2_mc(s.sa[st.idx] + pi * (kSaBytes / 2), &tm_sfa, &s.full[st.idx], 0, sfa_row + 4 * kb + 2 * pi, mask_a);
-                    } else {
-                        tma_load_2d_cg2(s.a[st.idx], &tm_act, &s.full[st.idx], kb * 128, m0);
-                        tma_load_2d_cg2(s.sa[st.idx], &tm_sfa, &s.full[st.idx], 0, sfa_row + 4 * kb);
+                    if (p.prof) NB200_TIMED(t_empty, mbar_wait(&s.empty[st.idx], st.phase ^ 1));
+                    else mbar_wait(&s.empty[st.idx], st.phase ^ 1);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(&s.full[st.idx], 2 * kStageBytes);
+                        if constexpr (kPairs == 2) {
+                            // half of the A rows / activation scale blocks, multicast to the CTA with the same q in the other pair
+                            tma_load_2d_cg2_mc(s.a[st.idx] + pi * (kABytes / 2), &tm_act, &s.full[st.idx], kb * 128, m0 + pi * (BM / 2), mask_a);
+                            tma_load_2d_cg2_mc(s.sa[st.idx] + pi * (kSaBytes / 2), &tm_sfa, &s.full[st.idx], 0, sfa_row + 4 * kb + 2 * pi, mask_a);
+                        } else {
+                            tma_load_2d_cg2(s.a[st.idx], &tm_act, &s.full[st.idx], kb * 128, m0);
+                            tma_load_2d_cg2(s.sa[st.idx], &tm_sfa, &s.full[st.idx], 0, sfa_row + 4 * kb);
+                        }
+                        tma_load_2d_cg2(s.b[st.idx], &tm_wgt, &s.full[st.idx], kb * 128, nh);
+                        if constexpr (kPairs == 2) {
+                            // weight scale factors of columns [n0 + 128 q, +128), multicast to both CTAs of the pair
+                            tma_load_2d_cg2_mc(s.sb[st.idx] + q * (kSbBytes / 2), &tm_sfb, &s.full[st.idx], 0, sfb_row + 4 * kb, mask_pair);
+                        } else {
+                            // one pair per cluster: each CTA fetches the scale factors of all 256 columns itself -- measured ~4 % faster than
+                            // splitting them and multicasting inside the pair (tools/gemm_ablate.py, r02)
+                            tma_load_2d_cg2(s.sb[st.idx], &tm_sfb, &s.full[st.idx], 0, (n0 / 128) * k64_total + 4 * kb);
+                            tma_load_2d_cg2(s.sb[st.idx] + kSbBytes / 2, &tm_sfb, &s.full[st.idx], 0, (n0 / 128 + 1) * k64_total + 4 * kb);
+                        }
                     }
-                    tma_load_2d_cg2(s.b[st.idx], &tm_wgt, &s.full[st.idx], kb * 128, nh);
-                    if constexpr (kPairs == 2) {
-                        // weight scale factors of columns [n0 + 128 q, +128), multicast to both CTAs of the pair
-                        tma_load_2d_cg2_mc(s.sb[st.idx] + q * (kSbBytes / 2), &tm_sfb, &s.full[st.idx], 0, sfb_row + 4 * kb, mask_pair);
-                    } else {
-                        // one pair per cluster: each CTA fetches the scale factors of all 256 columns itself -- measured ~4 % faster than
-                        // splitting them and multicasting inside the pair (tools/gemm_ablate.py, r02)
-                        tma_load_2d_cg2(s.sb[st.idx], &tm_sfb, &s.full[st.idx], 0, (n0 / 128) * k64_total + 4 * kb);
-                        tma_load_2d_cg2(s.sb[st.idx] + kSbBytes / 2, &tm_sfb, &s.full[st.idx], 0, (n0 / 128 + 1) * k64_total + 4 * kb);
-                    }
+                    __syncwarp();
                     st.advance();
                 }
                 for (int c = 0; c < lora_chunks; c++) {
                     mbar_wait(&s.lora_empty, lora_phase ^ 1);
-                    if (leader) mbar_expect_tx(&s.lora_b_full, 2 * BH * kLoraChunk * 2);
-                    // lora_up blocks [Rp/32][N/8][4][8][8] viewed as rows of 256 hT: row = chunk * N/8 + n/8
-                    tma_load_2d_cg2(s.lora_b, &tm_lu, &s.lora_b_full, 0, c * (p.N >> 3) + (nh >> 3));
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(&s.lora_b_full, 2 * BH * kLoraChunk * 2);
+                        // lora_up blocks [Rp/32][N/8][4][8][8] viewed as rows of 256 hT: row = chunk * N/8 + n/8
+                        tma_load_2d_cg2(s.lora_b, &tm_lu, &s.lora_b_full, 0, c * (p.N >> 3) + (nh >> 3));
+                    }
+                    __syncwarp();
                     lora_phase ^= 1;
                 }
             }
-            if (p.prof) p.prof[blockIdx.x * 16 + 0] = t_empty;
+            if (p.prof && lane == 0) p.prof[blockIdx.x * 16 + 0] = t_empty;
+        }
+    } else if (warp == 1 && leader && (p.debug & ~12288) == 0 && (p.prof == nullptr || (p.debug & 4096))) {
+        // ==================================== MMA issuer (pair leaders), hot path ======================
+        // ONE thread feeds the tensor pipe: 12 tcgen05.cp + 4 tcgen05.mma + 1 commit per 512 clk of MMA time, so every cycle it spends
+        // on anything else starves the pipe (timeline of tools/gemm_prof.py, r02a: 618 clk to issue a stage + 290 clk in an already
+        // satisfied barrier wait = the 930 clk stage period).  Here the WHOLE WARP runs the loops and polls the barriers (uniform control
+        // flow: loop state, descriptors and TMEM addresses live in uniform registers, no R2UR in front of every tcgen05 operand) and one
+        // elected lane issues; descriptors are base + slot * stride; no clock reads, no debug branches.
+        PipeState st;
+        uint32_t lora_phase = 0, acc_phase = 0;
+        constexpr uint32_t idesc_main = make_idesc_nvf4(2 * BM, BN);
+        constexpr uint32_t idesc_lora = make_idesc_f16(Tr::kIsBf16, 2 * BM, BN);
+        const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(s.a[0])), bdesc0 = make_sw128_kmajor_desc(smem_u32(s.b[0]));
+        const uint64_t sadesc0 = make_smem_desc(smem_u32(s.sa[0]), 0, 128, kLayoutNoSwizzle);
+        const uint64_t sbdesc0 = make_smem_desc(smem_u32(s.sb[0]), 0, 128, kLayoutNoSwizzle);
+        const uint64_t ladesc0 = make_smem_desc(smem_u32(s.lora_a), 128, 512, kLayoutNoSwizzle);
+        const uint64_t lbdesc0 = make_smem_desc(smem_u32(s.lora_b), 128, 512, kLayoutNoSwizzle);
+        const uint32_t tmem_d = tmem_base;
+        // NB200_GEMM_DEBUG=4096 + a prof buffer: timeline of block 0's issuing lane (tools/gemm_prof.py --timeline), otherwise untouched
+        long long *tl = ((p.debug & 4096) && p.prof != nullptr && blockIdx.x == 0) ? p.prof + 160 * 16 : nullptr;
+        int tli = 0;
+        const long long t_tl0 = clock64();
+        auto mark = [&](int tag) {
+            if (tl != nullptr && tli < 255) tl[tli++] = ((clock64() - t_tl0) << 4) | tag;
+        };
+        const bool cluster_acq = (p.debug & 8192) != 0;
+        for (int ct = cluster_id; ct < p.num_ct; ct += num_clusters) {
+            if (lane == 0) mark(1);
+            if (cluster_acq) mbar_wait_cluster(&s.tmem_empty, acc_phase ^ 1);
+            else mbar_wait(&s.tmem_empty, acc_phase ^ 1);
+            if (lane == 0) mark(2);
+            tc_fence_after_sync();
+            for (int kb = 0; kb < num_kblocks; kb++) {
+                const int nj = min(4, k64_total - 4 * kb);
+                const uint32_t sf_set = tmem_base + (kb & 1) * kSfSet;   // two scale-factor sets in TMEM (k-block parity)
+                // CTA-scope acquire on every wait of this warp: what it orders is async-proxy work (TMA writes, tcgen05 reads) and the
+                // peer's fence.proxy.async precedes its arrive, the same contract CUTLASS's ClusterBarrier::wait relies on; a satisfied
+                // cluster-scope try_wait costs ~250 clk on the issuing thread every stage (profiles/r02_issue_timeline.md); bit 8192 = old way
+                if (cluster_acq) mbar_wait_cluster(&s.full[st.idx], st.phase);
+                else mbar_wait(&s.full[st.idx], st.phase);
+                if (lane == 0) mark(3);
+                tc_fence_after_sync();
+                if (elect_one()) {
+                    const uint64_t ad = adesc0 + static_cast<uint64_t>(st.idx) * (kABytes >> 4), bd = bdesc0 + static_cast<uint64_t>(st.idx) * (kBBytes >> 4);
+                    const uint64_t sad = sadesc0 + static_cast<uint64_t>(st.idx) * (kSaBytes >> 4), sbd = sbdesc0 + static_cast<uint64_t>(st.idx) * (kSbBytes >> 4);
+                    if (nj == 4) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            tc_cp_32x128b_warpx4_cg2(sf_set + kTmemSfa + 4 * j, sad + 32 * j);
+                            tc_cp_32x128b_warpx4_cg2(sf_set + kTmemSfa + 16 + 8 * j, sbd + 32 * j);
+                            tc_cp_32x128b_warpx4_cg2(sf_set + kTmemSfa + 16 + 8 * j + 4, sbd + 128 + 32 * j);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            tc_mma_nvf4_cg2(tmem_d, ad + 2 * j, bd + 2 * j, idesc_main, sf_set + kTmemSfa + 4 * j, sf_set + kTmemSfa + 16 + 8 * j, (kb | j) != 0);
+                    } else {   // K tail
+                        for (int j = 0; j < nj; j++) {
+                            tc_cp_32x128b_warpx4_cg2(sf_set + kTmemSfa + 4 * j, sad + 32 * j);
+                            tc_cp_32x128b_warpx4_cg2(sf_set + kTmemSfa + 16 + 8 * j, sbd + 32 * j);
+                            tc_cp_32x128b_warpx4_cg2(sf_set + kTmemSfa + 16 + 8 * j + 4, sbd + 128 + 32 * j);
+                        }
+                        for (int j = 0; j < nj; j++)
+                            tc_mma_nvf4_cg2(tmem_d, ad + 2 * j, bd + 2 * j, idesc_main, sf_set + kTmemSfa + 4 * j, sf_set + kTmemSfa + 16 + 8 * j, (kb | j) != 0);
+                    }
+                    tc_commit_cg2(&s.empty[st.idx], kMaskAll);
+                }
+                __syncwarp();
+                if (lane == 0) mark(4);
+                st.advance();
+            }
+            for (int c = 0; c < lora_chunks; c++) {
+                mbar_wait(&s.lora_b_full, lora_phase);
+                if (cluster_acq) mbar_wait_cluster(&s.lora_a_full, lora_phase);
+                else mbar_wait(&s.lora_a_full, lora_phase);
+                tc_fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < kLoraChunk / 16; j++) tc_mma_f16_cg2(tmem_d, ladesc0 + 16 * j, lbdesc0 + 16 * j, idesc_lora, 1);
+                    tc_commit_cg2(&s.lora_empty, mask_pair);
+                }
+                __syncwarp();
+                lora_phase ^= 1;
+            }
+            if (elect_one()) tc_commit_cg2(&s.tmem_full, mask_pair);
+            __syncwarp();
+            acc_phase ^= 1;
         }
     } else if (warp == 1) {
-        // ==================================== MMA issuer (pair leaders) ===============================
+        // ============ MMA issuer, instrumented path (profiling counters / ablation bits): one thread, clock reads around the waits =======
         if (leader && elect_one()) {
             PipeState st;
             st.n = ring;
@@ -255,17 +351,28 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
             const long long t_mma0 = clock64();
             constexpr uint32_t idesc_main = make_idesc_nvf4(2 * BM, BN);
             constexpr uint32_t idesc_lora = make_idesc_f16(Tr::kIsBf16, 2 * BM, BN);
+            constexpr bool lean = false;
+            // timeline of block 0 (tools/gemm_prof.py --timeline): clock after each wait, 256 slots behind the per-CTA counters
+            long long *tl = (p.prof && blockIdx.x == 0) ? p.prof + 160 * 16 : nullptr;
+            int tli = 0;
+            auto mark = [&](int tag) {
+                if (tl && tli < 255) tl[tli++] = ((clock64() - t_mma0) << 4) | tag;
+            };
             for (int ct = cluster_id; ct < p.num_ct; ct += num_clusters) {
-                NB200_TIMED(t_tmem_empty, mbar_wait_cluster(&s.tmem_empty, acc_phase ^ 1));
+                mark(1);
+                if (lean) mbar_wait_cluster(&s.tmem_empty, acc_phase ^ 1);
+                else NB200_TIMED(t_tmem_empty, mbar_wait_cluster(&s.tmem_empty, acc_phase ^ 1));
+                mark(2);
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base;
                 for (int kb = 0; kb < num_kblocks; kb++) {
-                    if (!(p.debug & 32)) NB200_TIMED(t_full, mbar_wait_cluster(&s.full[st.idx], st.phase));
-                    if (t_first == 0) t_first = clock64() - t_mma0;
-                    tc_fence_after_sync();
                     const int nj = min(4, k64_total - 4 * kb);
                     // two scale-factor sets in TMEM (k-block parity): the copies of stage s+1 do not wait for the MMAs of stage s
                     const uint32_t sf_set = tmem_base + (kb & 1) * kSfSet;
+                    if (!(p.debug & 32)) NB200_TIMED(t_full, mbar_wait_cluster(&s.full[st.idx], st.phase));
+                    mark(3);
+                    if (t_first == 0) t_first = clock64() - t_mma0;
+                    tc_fence_after_sync();
                     for (int j = 0; j < ((p.debug & 16) ? 0 : nj); j++) {
                         tc_cp_32x128b_warpx4_cg2(sf_set + kTmemSfa + 4 * j, make_smem_desc(smem_u32(s.sa[st.idx] + j * 512), 0, 128, kLayoutNoSwizzle));
 #pragma unroll
@@ -278,11 +385,17 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                         tc_mma_nvf4_cg2(tmem_d, make_sw128_kmajor_desc(a_addr + j * 32), make_sw128_kmajor_desc(b_addr + j * 32), idesc_main,
                                         sf_set + kTmemSfa + 4 * j, sf_set + kTmemSfa + 16 + 8 * j, (kb | j) != 0);
                     tc_commit_cg2(&s.empty[st.idx], kMaskAll);
+                    mark(4);
                     st.advance();
                 }
                 for (int c = 0; c < lora_chunks; c++) {
-                    NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_b_full, lora_phase));
-                    NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_a_full, lora_phase));
+                    if (lean) {
+                        mbar_wait_cluster(&s.lora_b_full, lora_phase);
+                        mbar_wait_cluster(&s.lora_a_full, lora_phase);
+                    } else {
+                        NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_b_full, lora_phase));
+                        NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_a_full, lora_phase));
+                    }
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem_u32(s.lora_a), b_addr = smem_u32(s.lora_b);
 #pragma unroll
@@ -519,8 +632,11 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
     tc_fence_before_sync();
     cluster_sync();
     if (p.prof && threadIdx.x == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
         p.prof[blockIdx.x * 16 + 9] = clock64() - t_kernel0;
         p.prof[blockIdx.x * 16 + 12] = t_setup;
+        p.prof[blockIdx.x * 16 + 14] = static_cast<long long>(ns1 - ns_kernel0);   // wall time of this CTA: effective SM clock = slot 9 / slot 14
     }
     if (warp == 2) {
         tc_fence_after_sync();

@@ -357,12 +357,42 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             const long long t_mma0 = clock64();
             constexpr uint32_t idesc_main = FP4 ? make_idesc_nvf4(BM, BN) : make_idesc_f16(Tr::kIsBf16, BM, BN);
             constexpr uint32_t idesc_lora = make_idesc_f16(Tr::kIsBf16, BM, BN);
+            [[maybe_unused]] const bool lean = p.prof == nullptr && p.debug == 0;
+            [[maybe_unused]] const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(s.a[0])), bdesc0 = make_sw128_kmajor_desc(smem_u32(s.b[0]));
+            [[maybe_unused]] const uint64_t sadesc0 = make_smem_desc(smem_u32(s.sa[0]), 0, 128, kLayoutNoSwizzle);
+            [[maybe_unused]] const uint64_t sbdesc0 = make_smem_desc(smem_u32(s.sb[0]), 0, 128, kLayoutNoSwizzle);
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, it++) {
                 const int acc = it % C::kNumAcc;
                 NB200_TIMED(t_tmem_empty, mbar_wait(&s.tmem_empty[acc], acc_phase[acc] ^ 1));
                 tc_fence_after_sync();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kblocks; kb++) {
+                    if constexpr (FP4 && C::kK64 == 4) {
+                        // Hot path (no profiling counters, no ablation bits, full k block): this ONE thread feeds the tensor pipe, so
+                        // descriptors are base + slot * stride, the copies and MMAs are unrolled and there are no clock reads (r02:
+                        // the timeline of the cluster kernel showed 618 clk to issue a stage against 512 clk of MMA time).
+                        if (lean && k64_total - C::kK64 * kb >= 4) {
+                            mbar_wait(&s.full[st.idx], st.phase);
+                            tc_fence_after_sync();
+                            const uint32_t sf_set = tmem_base + (kb & 1) * C::kSfSet;
+                            const uint64_t ad = adesc0 + static_cast<uint64_t>(st.idx) * (C::kABytes >> 4), bd = bdesc0 + static_cast<uint64_t>(st.idx) * (C::kBBytes >> 4);
+                            const uint64_t sad = sadesc0 + static_cast<uint64_t>(st.idx) * ((C::kK64 * 512) >> 4);
+                            const uint64_t sbd = sbdesc0 + static_cast<uint64_t>(st.idx) * (((BN / 128) * C::kK64 * 512) >> 4);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                tc_cp_32x128b_warpx4(sf_set + C::kTmemSfa + 4 * j, sad + 32 * j);
+#pragma unroll
+                                for (int h = 0; h < BN / 128; h++)
+                                    tc_cp_32x128b_warpx4(sf_set + C::kTmemSfb + (BN / 32) * j + 4 * h, sbd + h * ((C::kK64 * 512) >> 4) + 32 * j);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                tc_mma_nvf4(tmem_d, ad + 2 * j, bd + 2 * j, idesc_main, sf_set + C::kTmemSfa + 4 * j, sf_set + C::kTmemSfb + (BN / 32) * j, (kb | j) != 0);
+                            tc_commit(&s.empty[st.idx]);
+                            st.advance(C::kStages);
+                            continue;
+                        }
+                    }
                     if constexpr (FP4) {
                         NB200_TIMED(t_full, mbar_wait(&s.full[st.idx], st.phase));
                         if (t_first == 0) t_first = clock64() - t_mma0;

@@ -291,7 +291,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kblocks; kb++) {
                     if constexpr (FP4) {
-                        NB200_TIMED(t_full, mbar_wait_cluster(&s.full[st.idx], st.phase));
+                        NB200_TIMED(t_full, mbar_wait(&s.full[st.idx], st.phase));   // TMA barrier: CTA-scope acquire (see gemm_nvfp4_cluster.cu)
                         if (t_first == 0) t_first = clock64() - t_mma0;
                         tc_fence_after_sync();
                         const int nj = min(4, k64_total - 4 * kb);

@@ -4,12 +4,16 @@
 // v1 streamed rows straight into registers and was latency bound (16 % of HBM peak, ncu
 // profiles/r01_quantize.txt: 8 resident warps, 30 % issue active, loads serialised behind math).
 // v2 decouples memory from math:
-//   * one elected producer thread keeps a 16-deep ring of TMA tiles in flight per CTA
+//   * one elected producer thread keeps a deep ring of TMA tiles in flight per CTA
 //     (cp.async.bulk.tensor.2d, [32 rows x 64 k] = one quantisation group per row, 128B swizzle,
-//     rows >= M are zero-filled by the tensor map) -> 64 KB outstanding per SM without a register;
-//   * 8 consumer warps take the groups round-robin: ldmatrix.x4 A fragments + mma.sync.m16n8k16
+//     rows >= M are zero-filled by the tensor map) -> ~100 KB outstanding per SM without a register;
+//   * a second producer thread streams the matching lora_down fragments (4 KB per group, cp.async.bulk) through their own
+//     ring, released right after the MMAs: r01/early r02 fetched them with LDGs in the consumer warps, two exposed L2 round
+//     trips per group on every warp (the launch was latency bound: 22 us at M=4096 K=3072 against a 4.5 us HBM floor);
+//   * consumer warps take the groups round-robin: ldmatrix.x4 A fragments + mma.sync.m16n8k16
 //     for x @ lora_down^T (fp32), then the per-row absmax / 4-bit rounding with the reference's exact
-//     instruction recipe, 8 lanes per row so a warp store covers 32 contiguous bytes per row;
+//     instruction recipe, one lane per row;
+//   * the per-warp partial projections are summed by a fixed binary tree over the warps (deterministic, 4 KB per warp pair);
 //   * optional split of K across CTAs (small M): per-split partial projections go to a workspace and
 //     the LAST CTA of a row block (atomic ticket) sums them in split order -> still deterministic.
 #include <cuda.h>
@@ -25,9 +29,10 @@ using namespace ptx;
 
 constexpr int kRows = 32;
 constexpr int kTileBytes = kRows * 128;
-// Two shapes of the same kernel (template parameters kConsumers consumer warps, kStages ring slots of 4 KB):
-//   <16, 32>  one CTA per SM (default): 200 KB of shared memory, 128 KB of TMA traffic in flight per SM
-//   < 8, 16>  TWO CTAs per SM + K split (NB200_QUANT_CFG=1): 2 x 148 CTA slots, 128 row blocks x 2 K halves for the 4096-row
+constexpr int kBBytes = 4096;   // lora_down fragments of one group and one 32-rank chunk: 2 k-halves x 4 rank blocks x 32 lanes x 16 B
+// Two shapes of the same kernel (template parameters: kConsumers consumer warps, kStages x-ring slots, kConsumers B-ring slots):
+//   <16, 28>  one CTA per SM (default): 112 KB of activations + 64 KB of fragments in flight per SM
+//   < 8, 14>  TWO CTAs per SM + K split (NB200_QUANT_CFG=1): 2 x 148 CTA slots, 128 row blocks x 2 K halves for the 4096-row
 //             activations instead of 128 CTAs on 148 SMs.  Measured SLOWER on B200 (r02, tools/op_sweep.py on one box: 26.7 vs
 //             22.5 us at M=4096 K=3072, 62.5 vs 55-59 us at K=12288): the split's workspace round trip + ticket + last-CTA
 //             reduction cost more than the idle 20 SMs; kept as an ablation switch
@@ -41,18 +46,23 @@ struct Q2Params {
     float *ws_partial;  // [KS][Mp][32] per rank chunk, or null when KS == 1
     unsigned int *ws_ticket;  // [Mp / 32]
     int M, Mp, K, R, Rp, KS;
-    int debug;            // NB200_QUANT_DEBUG ablation bits (results invalid): 1 = skip the low-rank MMAs, 2 = skip the quantise phases
+    int debug;            // NB200_QUANT_DEBUG ablation bits (results invalid): 1 = skip the low-rank MMAs, 2 = skip the quantise phases,
+                          // 4 = compute but do not store codes / scales, 8 = no activation loads (consumers run on whatever the ring holds),
+                          // 16 = return after the barrier setup, 32 = return at once
     int unsigned_shift;   // INT4: quantise (x + 0.171875) / smooth to unsigned codes (scale = max / 15)
 };
 
 template <int kConsumers, int kStages>
 struct alignas(1024) Q2Smem {
     alignas(1024) uint8_t tile[kStages][kTileBytes];
-    float red[kConsumers][kRows][33];
+    alignas(128) uint8_t bfrag[kConsumers][kBBytes];
+    alignas(16) float red[kConsumers / 2][32][32];   // tree reduction: [warp of the upper half][8 float4 per lane, lane-interleaved]
     alignas(16) float rsm[kConsumers][64];   // per warp: reciprocals of the current group's smoothing factors
     alignas(16) float ksm[kConsumers][64];   // per warp: 2^24 pre-scale for denormal factors (slow path only)
     uint64_t full[kStages];
     uint64_t empty[kStages];
+    uint64_t bfull[kConsumers];
+    uint64_t bempty[kConsumers];
     unsigned int is_last;
 };
 
@@ -94,7 +104,7 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, const uint32_t (&w)[4]) {
 }
 
 template <typename hT, bool FP4, int kConsumers, int kStages>
-__global__ void __launch_bounds__((kConsumers + 1) * 32, kConsumers == 8 ? 2 : 1)
+__global__ void __launch_bounds__((kConsumers + 2) * 32, kConsumers == 8 ? 2 : 1)
 quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
     using Tr = HalfTraits<hT>;
     using T2 = typename Tr::T2;
@@ -117,21 +127,27 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
     const int nt_total = p.Rp >> 3;
     const bool has_lora = p.Rp > 0;
 
+    if (p.debug & 32) return;   // ablation: launch cost alone
     if (threadIdx.x == 0) {
         prefetch_tensormap(&tm_x);
         for (int i = 0; i < kStages; i++) {
             mbar_init(&s.full[i], 1);
             mbar_init(&s.empty[i], 1);
         }
+        for (int i = 0; i < kConsumers; i++) {
+            mbar_init(&s.bfull[i], 1);
+            mbar_init(&s.bempty[i], 1);
+        }
         fence_mbar_init();
     }
     __syncthreads();
     griddep_launch_dependents();
     griddep_wait();   // x is the previous kernel's output
+    if (p.debug & 16) return;   // ablation: launch + barrier setup alone
 
     if (warp == kConsumers) {
         // ============================ TMA producer ==============================================
-        if (elect_one()) {
+        if (!(p.debug & 8) && elect_one()) {
             uint32_t it = 0;
             for (int chunk = 0; chunk < n_chunks; chunk++) {
                 for (int i = 0; i < n_groups; i++, it++) {
@@ -142,12 +158,30 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                 }
             }
         }
+    } else if (warp == kConsumers + 1) {
+        // ============================ lora_down fragment producer (weights: no dependence on the previous kernel's output) =========
+        if (has_lora && elect_one()) {
+            const uint8_t *ldb = reinterpret_cast<const uint8_t *>(p.ld);
+            uint32_t it = 0;
+            for (int chunk = 0; chunk < n_chunks; chunk++) {
+                for (int i = 0; i < n_groups; i++, it++) {
+                    const uint32_t st = it % kConsumers, ph = (it / kConsumers) & 1;
+                    mbar_wait(&s.bempty[st], ph ^ 1);
+                    mbar_expect_tx(&s.bfull[st], kBBytes);
+#pragma unroll
+                    for (int kb = 0; kb < 2; kb++)
+                        bulk_load(s.bfrag[st] + kb * (kBBytes / 2), ldb + (static_cast<size_t>((g_begin + i) * 2 + kb) * nt_total + chunk * 4) * 512, kBBytes / 2,
+                                  &s.bfull[st]);
+                }
+            }
+        }
     } else {
         // ============================ consumers ==================================================
         const int gq = lane >> 2, t = lane & 3;   // mma fragment coordinates
         const hT *smooth = reinterpret_cast<const hT *>(p.smooth);
-        const uint4 *ldw = reinterpret_cast<const uint4 *>(p.ld);
         uint32_t it_base = 0;
+        uint32_t sw_next = 0;   // smoothing factors of the NEXT group of this warp (columns 2 lane, 2 lane + 1), fetched one group ahead
+        if (smooth != nullptr && warp < n_groups) sw_next = *reinterpret_cast<const uint32_t *>(smooth + (g_begin + warp) * 64 + 2 * lane);
         for (int chunk = 0; chunk < n_chunks; chunk++, it_base += n_groups) {
             float acc[2][4][4];
 #pragma unroll
@@ -161,18 +195,15 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                 const int g = g_begin + i;
                 const uint32_t it = it_base + i;
                 const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-                // B fragments (L2 resident) and smoothing factors first: independent of the tile
-                uint4 bw[4];   // B fragments of the first 32-wide half; the second half is fetched after it is consumed
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    bw[j] = has_lora ? ldg_v4(ldw + (static_cast<size_t>(g * 2) * nt_total + chunk * 4 + j) * 32 + lane) : make_uint4(0, 0, 0, 0);
+                const uint32_t bst = it % kConsumers, bph = (it / kConsumers) & 1;
                 // x / smooth as the reference's __fdividef computes it (gemm_utils.cuh:329-344): SASS is
                 // "if |b| < 2^-126 scale a and b by 2^24; MUFU.RCP(b) * a".  The reciprocal and the scale depend
                 // only on the column, so they are hoisted out of the 8 row passes of the tile.
                 bool any_tiny = false;
                 if (chunk == 0 && smooth != nullptr) {
                     // lane l owns columns 2l, 2l+1 of the group; every lane (= row) reads all 64 back below
-                    const uint32_t sw = *reinterpret_cast<const uint32_t *>(smooth + g * 64 + 2 * lane);
+                    const uint32_t sw = sw_next;
+                    if (i + kConsumers < n_groups) sw_next = *reinterpret_cast<const uint32_t *>(smooth + (g + kConsumers) * 64 + 2 * lane);
                     const float2 b = Tr::to_float2(*reinterpret_cast<const T2 *>(&sw));
                     const float bb[2] = {b.x, b.y};
                     __syncwarp();   // the previous tile's readers are done with s.rsm[warp]
@@ -188,35 +219,39 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                 const bool slow_div = __any_sync(0xffffffffu, any_tiny);
                 __syncwarp();   // s.rsm / s.ksm visible to every lane
 
-                mbar_wait(&s.full[st], ph);
+                if (!(p.debug & 8)) mbar_wait(&s.full[st], ph);
                 const uint32_t tile = smem_u32(s.tile[st]);
 
                 // ---- x @ lora_down^T on the un-smoothed tile (lora.cuh:243-353) ---------------------
+                if (has_lora) {
+                    mbar_wait(&s.bfull[bst], bph);
+                    const uint32_t bbase = smem_u32(s.bfrag[bst]) + lane * 16;
 #pragma unroll
-                for (int kb = 0; kb < (((p.debug & 1) || !has_lora) ? 0 : 2); kb++) {
+                    for (int kb = 0; kb < ((p.debug & 1) ? 0 : 2); kb++) {
+                        uint4 bw[4];
 #pragma unroll
-                    for (int m = 0; m < 2; m++) {
+                        for (int j = 0; j < 4; j++) bw[j] = lds_v4(bbase + (kb * 4 + j) * 512);
 #pragma unroll
-                        for (int k2 = 0; k2 < 2; k2++) {
-                            const int kstep = kb * 2 + k2;
-                            const int r = m * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-                            const int ch = kstep * 2 + (lane >> 4);
-                            uint32_t a[4];
-                            ldmatrix_x4(tile + r * 128 + ((ch ^ (r & 7)) << 4), a);
+                        for (int m = 0; m < 2; m++) {
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                if (k2)
-                                    mma16816<hT>(acc[m][j], a, bw[j].z, bw[j].w);
-                                else
-                                    mma16816<hT>(acc[m][j], a, bw[j].x, bw[j].y);
+                            for (int k2 = 0; k2 < 2; k2++) {
+                                const int kstep = kb * 2 + k2;
+                                const int r = m * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+                                const int ch = kstep * 2 + (lane >> 4);
+                                uint32_t a[4];
+                                ldmatrix_x4(tile + r * 128 + ((ch ^ (r & 7)) << 4), a);
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    if (k2)
+                                        mma16816<hT>(acc[m][j], a, bw[j].z, bw[j].w);
+                                    else
+                                        mma16816<hT>(acc[m][j], a, bw[j].x, bw[j].y);
+                                }
                             }
                         }
                     }
-                    if (kb == 0) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            bw[j] = ldg_v4(ldw + (static_cast<size_t>(g * 2 + 1) * nt_total + chunk * 4 + j) * 32 + lane);
-                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s.bempty[bst]);
                 }
 
                 // ---- smooth + quantise: 8 lanes per row, 4 rows per pass (gemm_w4a4.cuh:85-187,429-523) --
@@ -347,8 +382,12 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                                 words[j] = p.unsigned_shift ? pack8_int4_b200<true>(qv) : pack8_int4_b200<false>(qv);
                             }
                         }
-                        *reinterpret_cast<uint4 *>(qdst) = make_uint4(words[0], words[1], words[2], words[3]);
-                        *reinterpret_cast<uint4 *>(qdst + 16) = make_uint4(words[4], words[5], words[6], words[7]);
+                        if (!(p.debug & 4)) {
+                            *reinterpret_cast<uint4 *>(qdst) = make_uint4(words[0], words[1], words[2], words[3]);
+                            *reinterpret_cast<uint4 *>(qdst + 16) = make_uint4(words[4], words[5], words[6], words[7]);
+                        } else if (words[0] == 0x12345678u && words[3] == 0x9abcdef0u) {   // keep the computation alive
+                            *reinterpret_cast<uint32_t *>(qdst) = words[1] ^ words[2] ^ words[4] ^ words[5] ^ words[6] ^ words[7];
+                        }
                     } else {
                         uint32_t words[8];
                         uint32_t sfw = 0;
@@ -385,11 +424,15 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                                 words[g16 * 2 + w2] = wv;
                             }
                         }
-                        *reinterpret_cast<uint4 *>(qdst) = make_uint4(words[0], words[1], words[2], words[3]);
-                        *reinterpret_cast<uint4 *>(qdst + 16) = make_uint4(words[4], words[5], words[6], words[7]);
                         uint8_t *sf = reinterpret_cast<uint8_t *>(p.scales) + (static_cast<size_t>(m >> 7) * G + g) * 512 + (m & 31) * 16 +
                                       ((m & 127) >> 5) * 4;
-                        *reinterpret_cast<uint32_t *>(sf) = sfw;
+                        if (!(p.debug & 4)) {
+                            *reinterpret_cast<uint4 *>(qdst) = make_uint4(words[0], words[1], words[2], words[3]);
+                            *reinterpret_cast<uint4 *>(qdst + 16) = make_uint4(words[4], words[5], words[6], words[7]);
+                            *reinterpret_cast<uint32_t *>(sf) = sfw;
+                        } else if (sfw == 0x12345678u && words[3] == 0x9abcdef0u) {   // keep the computation alive
+                            *reinterpret_cast<uint32_t *>(sf) = words[0] ^ words[1] ^ words[2] ^ words[4] ^ words[5] ^ words[6] ^ words[7];
+                        }
                     }
                 }
                 if (chunk == 0 && (smooth != nullptr || (!FP4 && p.unsigned_shift))) fence_proxy_async_smem();   // our in-place writes vs the TMA refill of this stage
@@ -398,40 +441,59 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
             }
 
             if (!has_lora) continue;   // (uniform across the CTA)
-            // ---- fixed-order reduction of the per-warp partial projections --------------------------
+            // ---- fixed binary tree over the warps: round `half`: warps [half, 2 half) hand their fragments to warps [0, half) ------
 #pragma unroll
-            for (int m = 0; m < 2; m++)
+            for (int half = kConsumers / 2; half >= 1; half >>= 1) {
+                if (warp >= half && warp < 2 * half) {
+                    float4 *dst = reinterpret_cast<float4 *>(&s.red[warp - half][0][0]) + lane;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    s.red[warp][m * 16 + gq][j * 8 + t * 2] = acc[m][j][0];
-                    s.red[warp][m * 16 + gq][j * 8 + t * 2 + 1] = acc[m][j][1];
-                    s.red[warp][m * 16 + gq + 8][j * 8 + t * 2] = acc[m][j][2];
-                    s.red[warp][m * 16 + gq + 8][j * 8 + t * 2 + 1] = acc[m][j][3];
+                    for (int m = 0; m < 2; m++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dst[(m * 4 + j) * 32] = make_float4(acc[m][j][0], acc[m][j][1], acc[m][j][2], acc[m][j][3]);
                 }
-            named_bar_sync(1, kConsumers * 32);
-            const int ct = threadIdx.x;  // 0..255
-            float sum[kRows * 32 / (kConsumers * 32)];
+                named_bar_sync(1, kConsumers * 32);
+                if (warp < half) {
+                    const float4 *src = reinterpret_cast<const float4 *>(&s.red[warp][0][0]) + lane;
 #pragma unroll
-            for (int u = 0; u < kRows * 32 / (kConsumers * 32); u++) {
-                const int idx = ct + u * kConsumers * 32;
-                const int rr = idx >> 5, cc = idx & 31;
-                float v = 0.f;
+                    for (int m = 0; m < 2; m++)
 #pragma unroll
-                for (int w = 0; w < kConsumers; w++) v += s.red[w][rr][cc];
-                sum[u] = v;
+                        for (int j = 0; j < 4; j++) {
+                            const float4 v = src[(m * 4 + j) * 32];
+                            acc[m][j][0] += v.x;
+                            acc[m][j][1] += v.y;
+                            acc[m][j][2] += v.z;
+                            acc[m][j][3] += v.w;
+                        }
+                }
+                named_bar_sync(1, kConsumers * 32);
             }
+            // warp 0 holds the sums in mma fragment order: (row m*16 + gq [+8], rank j*8 + 2t [+1])
+            [[maybe_unused]] const int ct = threadIdx.x;  // 0 .. kConsumers*32
             if (p.KS == 1) {
+                if (warp == 0) {
 #pragma unroll
-                for (int u = 0; u < kRows * 32 / (kConsumers * 32); u++) {
-                    const int idx = ct + u * kConsumers * 32;
-                    const int rr = idx >> 5, rank = chunk * 32 + (idx & 31);
-                    if (rank < p.R) p.lora[static_cast<size_t>(row0 + rr) * p.R + rank] = sum[u];
+                    for (int m = 0; m < 2; m++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+#pragma unroll
+                            for (int hh = 0; hh < 2; hh++) {
+                                const int rr = m * 16 + gq + hh * 8, rank = chunk * 32 + j * 8 + t * 2;
+                                if (rank < p.R)   // R is a multiple of 16: rank and rank + 1 are valid together
+                                    *reinterpret_cast<float2 *>(p.lora + static_cast<size_t>(row0 + rr) * p.R + rank) = make_float2(acc[m][j][2 * hh], acc[m][j][2 * hh + 1]);
+                            }
                 }
             } else {
                 // partial of this k split -> workspace; the last split to finish sums all of them in split order
                 float *mine = p.ws_partial + (static_cast<size_t>(ks) * p.Mp + row0) * 32;
+                if (warp == 0) {
 #pragma unroll
-                for (int u = 0; u < kRows * 32 / (kConsumers * 32); u++) mine[ct + u * kConsumers * 32] = sum[u];
+                    for (int m = 0; m < 2; m++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+#pragma unroll
+                            for (int hh = 0; hh < 2; hh++)
+                                *reinterpret_cast<float2 *>(mine + (m * 16 + gq + hh * 8) * 32 + j * 8 + t * 2) = make_float2(acc[m][j][2 * hh], acc[m][j][2 * hh + 1]);
+                }
                 __threadfence();
                 named_bar_sync(1, kConsumers * 32);
                 if (ct == 0) {
@@ -462,7 +524,7 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
 
 template <typename hT, bool FP4, int kConsumers, int kStages>
 static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
-    constexpr int kThreads = (kConsumers + 1) * 32;
+    constexpr int kThreads = (kConsumers + 2) * 32;
     CUtensorMap tm_x;
     const CUtensorMapDataType dt = HalfTraits<hT>::kIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     int rc = make_map_2d(&tm_x, dt, a.input, a.K, a.M, static_cast<uint64_t>(a.K) * 2, 64, kRows, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -479,8 +541,8 @@ static int launch_q2(const nb200_quantize_args &a, cudaStream_t stream) {
     p.R = a.R;
     p.Rp = (a.R + 31) / 32 * 32;
     p.unsigned_shift = a.act_unsigned_shift;
-    static const int dbg = getenv("NB200_QUANT_DEBUG") ? atoi(getenv("NB200_QUANT_DEBUG")) : 0;
-    p.debug = dbg;
+    const char *dbg_env = getenv("NB200_QUANT_DEBUG");   // read per launch: tools/quant_ablate.py sweeps it inside one process
+    p.debug = dbg_env ? atoi(dbg_env) : 0;
     // split K across CTAs whenever the row blocks alone would not fill every CTA slot of the chip
     const int row_blocks = a.Mp / kRows;
     const int G = a.K / 64;
@@ -512,11 +574,11 @@ int quantize_v2_dispatch(const nb200_quantize_args &a, cudaStream_t stream) {
     const bool bf16 = a.dtype == NB200_BF16;
     static const int cfg = getenv("NB200_QUANT_CFG") ? atoi(getenv("NB200_QUANT_CFG")) : 0;   // 0: one CTA per SM (default), 1: two CTAs per SM + K split
     if (cfg == 0) {
-        if (bf16) return a.fp4 ? launch_q2<__nv_bfloat16, true, 16, 32>(a, stream) : launch_q2<__nv_bfloat16, false, 16, 32>(a, stream);
-        return a.fp4 ? launch_q2<__half, true, 16, 32>(a, stream) : launch_q2<__half, false, 16, 32>(a, stream);
+        if (bf16) return a.fp4 ? launch_q2<__nv_bfloat16, true, 16, 28>(a, stream) : launch_q2<__nv_bfloat16, false, 16, 28>(a, stream);
+        return a.fp4 ? launch_q2<__half, true, 16, 28>(a, stream) : launch_q2<__half, false, 16, 28>(a, stream);
     }
-    if (bf16) return a.fp4 ? launch_q2<__nv_bfloat16, true, 8, 16>(a, stream) : launch_q2<__nv_bfloat16, false, 8, 16>(a, stream);
-    return a.fp4 ? launch_q2<__half, true, 8, 16>(a, stream) : launch_q2<__half, false, 8, 16>(a, stream);
+    if (bf16) return a.fp4 ? launch_q2<__nv_bfloat16, true, 8, 14>(a, stream) : launch_q2<__nv_bfloat16, false, 8, 14>(a, stream);
+    return a.fp4 ? launch_q2<__half, true, 8, 14>(a, stream) : launch_q2<__half, false, 8, 14>(a, stream);
 }
 
 }  // namespace nb200

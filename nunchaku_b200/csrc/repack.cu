@@ -107,7 +107,8 @@ __global__ void repack_channel_vector_kernel(const hT *__restrict__ src, void *_
 // (LBO = 128 B between the 4 rank-octets, SBO = 512 B between 8-row groups).
 template <typename hT>
 __global__ void repack_lora_up_kernel(const hT *__restrict__ src, hT *__restrict__ dst, const float *__restrict__ cscale,
-                                      int N, int R, int Rp) {
+                                      int N, int R, int Rp, int *__restrict__ bad_channel) {
+    constexpr float kMax = HalfTraits<hT>::kIsBf16 ? 3.38e38f : 65504.f;
     const size_t total = static_cast<size_t>(N) * Rp;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -121,7 +122,10 @@ __global__ void repack_lora_up_kernel(const hT *__restrict__ src, hT *__restrict
             const int ii = n >> 4, h = (n >> 3) & 1, g = n & 7;
             const int u = r >> 4, c = (r >> 3) & 1, t = (r >> 1) & 3, e = r & 1;
             v = HalfTraits<hT>::to_float(src[ref_lowrank_index(ii, u, g, t, h, c, e, R)]);
-            if (cscale != nullptr) v = v / cscale[n];
+            if (cscale != nullptr) {
+                v = v / cscale[n];
+                if (!(fabsf(v) <= kMax)) atomicMax(bad_channel, n + 1);   // zero / denormal / non-finite scale, or the quotient overflows hT
+            }
         }
         dst[i] = HalfTraits<hT>::from_float(v);
     }
@@ -238,14 +242,37 @@ extern "C" __attribute__((visibility("default"))) int nb200_repack_lora_up(const
     NB200_REQUIRE(dtype == NB200_FP16 || dtype == NB200_BF16, "dtype must be fp16 or bf16");
     const int Rp = (R + 31) / 32 * 32;
     const size_t total = static_cast<size_t>(N) * Rp;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // The epilogue computes (acc + lora) * cscale + bias on ONE accumulator, so the low-rank factor is stored divided by cscale
+    // (DESIGN.md section 4.2).  A channel whose scale is zero, denormal or non-finite, or whose quotient leaves hT's range, cannot be
+    // represented that way (the reference adds the low-rank term unscaled): detect it here, at load time, instead of producing inf / NaN
+    // at run time.  (Skipped while the stream is being captured: the check needs a device -> host read.)
+    int *bad_dev = nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NB200_CUDA_CHECK(cudaStreamIsCapturing(st, &cap));
+    const bool validate = cscale != nullptr && cap == cudaStreamCaptureStatusNone;
+    if (cscale != nullptr) {
+        NB200_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void **>(&bad_dev), sizeof(int), st));
+        NB200_CUDA_CHECK(cudaMemsetAsync(bad_dev, 0, sizeof(int), st));
+    }
     if (dtype == NB200_BF16)
-        repack_lora_up_kernel<__nv_bfloat16><<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            static_cast<const __nv_bfloat16 *>(src), static_cast<__nv_bfloat16 *>(dst), cscale, N, R, Rp);
+        repack_lora_up_kernel<__nv_bfloat16><<<grid_for(total), kThreads, 0, st>>>(static_cast<const __nv_bfloat16 *>(src), static_cast<__nv_bfloat16 *>(dst),
+                                                                                    cscale, N, R, Rp, bad_dev);
     else
-        repack_lora_up_kernel<__half><<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            static_cast<const __half *>(src), static_cast<__half *>(dst), cscale, N, R, Rp);
+        repack_lora_up_kernel<__half><<<grid_for(total), kThreads, 0, st>>>(static_cast<const __half *>(src), static_cast<__half *>(dst), cscale, N, R, Rp,
+                                                                             bad_dev);
     count_launch();
     NB200_CUDA_CHECK(cudaGetLastError());
+    int bad = 0;
+    if (validate) {
+        NB200_CUDA_CHECK(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NB200_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (bad_dev != nullptr) NB200_CUDA_CHECK(cudaFreeAsync(bad_dev, st));
+    if (bad != 0)
+        return fail(NB200_ERR_UNSUPPORTED, "repack_lora_up: output channel " + std::to_string(bad - 1) +
+                                               ": alpha * wcscales is zero / denormal / non-finite, or lora_up / (alpha * wcscales) overflows the 16-bit type; "
+                                               "the fused epilogue cannot represent this layer (use bf16, or rescale lora_up / lora_scales)");
     return NB200_OK;
 }
 

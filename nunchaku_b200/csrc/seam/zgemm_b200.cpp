@@ -17,6 +17,10 @@
 // and re-allocates some (lora_*, wcscales, lazy-load / offload: src/Linear.cpp:124-154, src/Module.h:96-131), so the
 // loader must drop stale entries: call nunchaku::kernels::b200_invalidate(dst) at the end of GEMM_W4A4::loadParam
 // (one line), or b200_invalidate_all() after a load_state_dict / LoRA update.
+// A device address alone does not identify a parameter when the caller is Python (torch's caching allocator hands a freed
+// weight's address to the next one): the pybind layer (pybind_ops.cpp) therefore tags every weight-side tensor of a call with
+// an identity token -- (live StorageImpl, version counter) -- through b200_set_identity(), and an entry whose token differs is
+// rebuilt.  C++ callers (Module-owned parameters, every change goes through loadParam) leave the token at 0.
 #include <cuda_runtime.h>
 
 #include <mutex>
@@ -57,7 +61,9 @@ struct Entry {
     float mul = 1.f;
     void *data = nullptr;
     size_t bytes = 0;
+    uint64_t token = 0;
 };
+thread_local std::unordered_map<const void *, uint64_t> t_identity;   // this call's weight tensors: device address -> identity token
 enum Kind { K_QWEIGHT, K_QWEIGHT_FP4, K_WSCALES, K_WSCALES_FP4, K_VEC_F32, K_VEC_HT, K_LORA_UP, K_LORA_DOWN, K_LORA_DOWN_NEXT, K_CONST };
 
 std::mutex g_mu;
@@ -79,10 +85,13 @@ template <typename Make>
 void *cached(const Tensor &src, int kind, size_t bytes, const void *dep, float mul, Make &&make) {
     std::lock_guard<std::mutex> lock(g_mu);
     const Key key{src.data_ptr(), kind, current_device()};
+    uint64_t token = 0;
+    if (auto id = t_identity.find(src.data_ptr()); id != t_identity.end()) token = id->second;
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
         Entry &e = it->second;
-        if (e.shape == src.shape.dataExtent && e.dtype == int(src.scalar_type()) && e.dep == dep && e.mul == mul && e.bytes == bytes) return e.data;
+        if (e.shape == src.shape.dataExtent && e.dtype == int(src.scalar_type()) && e.dep == dep && e.mul == mul && e.bytes == bytes && e.token == token)
+            return e.data;
         cudaFree(e.data);  // same address, different tensor: rebuild
         g_cache.erase(it);
     }
@@ -92,6 +101,7 @@ void *cached(const Tensor &src, int kind, size_t bytes, const void *dep, float m
     e.dep = dep;
     e.mul = mul;
     e.bytes = bytes;
+    e.token = token;
     checkCUDA(cudaMalloc(&e.data, bytes ? bytes : 1));
     make(e.data);
     g_cache.emplace(key, e);
@@ -181,6 +191,8 @@ void b200_invalidate(Tensor t) {
         }
     }
 }
+void b200_set_identity(const void *device_ptr, uint64_t token) { t_identity[device_ptr] = token; }
+void b200_clear_identities() { t_identity.clear(); }
 void b200_invalidate_all() {
     std::lock_guard<std::mutex> lock(g_mu);
     for (auto &kv : g_cache) cudaFree(kv.second.data);

@@ -93,14 +93,14 @@ echo "linked $OUT/libnunchaku_ref.so"
 
 # ---- oracle/_ref/libnunchaku_seam.so: the reference's UNMODIFIED host layer (src/Linear.cpp, Module.cpp, activation.cpp,
 # layernorm.cpp objects from above) on top of OUR definitions of the zgemm.h / misc_kernels.h / activation / layernorm
-# kernel entry points (nunchaku_b200/csrc/seam/*.cpp -> libnunchaku_b200.so).  gemv_awq is the reference's (row N2).
+# kernel entry points (nunchaku_b200/csrc/seam/*.cpp -> libnunchaku_b200.so), gemv_awq included (row N2: awq_b200.cpp).
 SEAM="$ROOT/nunchaku_b200/csrc/seam"
-for f in zgemm_b200 glue_b200; do
+for f in zgemm_b200 glue_b200 awq_b200; do
   g++ "${GCC_FLAGS[@]}" "${INC[@]}" -I "$ROOT/include" -c "$SEAM/$f.cpp" -o "$OBJ/seam_$f.o"
 done
 nvcc "${NVCC_FLAGS[@]}" "${INC[@]}" -DNREF_SEAM_BUILD=1 -c "$HERE/ref_shim.cu" -o "$OBJ/seam_shim.o"
 g++ -shared -o "$OUT/libnunchaku_seam.so" "$OBJ/src_Linear.o" "$OBJ/src_Module.o" "$OBJ/src_activation.o" "$OBJ/src_layernorm.o" \
-    "$OBJ/src_kernels_awq_gemv_awq.o" "$OBJ/seam_zgemm_b200.o" "$OBJ/seam_glue_b200.o" "$OBJ/seam_shim.o" \
+    "$OBJ/seam_awq_b200.o" "$OBJ/seam_zgemm_b200.o" "$OBJ/seam_glue_b200.o" "$OBJ/seam_shim.o" \
     -L"$ROOT/nunchaku_b200/_lib" -lnunchaku_b200 -L/usr/local/cuda/lib64 -lcudart -lcublas \
     -Wl,-rpath,/usr/local/cuda/lib64 -Wl,-rpath,'$ORIGIN/../../nunchaku_b200/_lib' -Wl,--no-undefined
 echo "linked $OUT/libnunchaku_seam.so"
@@ -122,7 +122,7 @@ if [ ! -f "$OBJ/py_torch_interop.o" ] || [ "$REF/src/interop/torch.cpp" -nt "$OB
   g++ "${TFLAGS[@]}" "${INC[@]}" -c "$REF/src/interop/torch.cpp" -o "$OBJ/py_torch_interop.o"
 fi
 g++ "${TFLAGS[@]}" "${INC[@]}" -I "$REF/nunchaku/csrc" -I "$ROOT/include" -c "$SEAM/pybind_ops.cpp" -o "$OBJ/py_pybind_ops.o"
-g++ -shared -o "$OUT/pyseam/_C.so" "$OBJ/py_pybind_ops.o" "$OBJ/py_torch_interop.o" "$OBJ/seam_zgemm_b200.o" "$OBJ/src_kernels_awq_gemv_awq.o" \
+g++ -shared -o "$OUT/pyseam/_C.so" "$OBJ/py_pybind_ops.o" "$OBJ/py_torch_interop.o" "$OBJ/seam_zgemm_b200.o" "$OBJ/seam_awq_b200.o" \
     -L"$ROOT/nunchaku_b200/_lib" -lnunchaku_b200 -L"$TORCH_LIB" -ltorch -ltorch_cpu -ltorch_cuda -lc10 -lc10_cuda -ltorch_python \
     -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,/usr/local/cuda/lib64 -Wl,-rpath,"$TORCH_LIB" -Wl,-rpath,'$ORIGIN/../../../nunchaku_b200/_lib'
 echo "linked $OUT/pyseam/_C.so"

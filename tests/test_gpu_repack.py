@@ -64,6 +64,48 @@ def test_lowrank(rp, dtype, R):
     assert torch.equal(got_dn, L.lora_down_frags(ld))
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_lora_up_division_by_the_channel_scale_is_validated_at_load_time(rp, dtype):
+    """the epilogue keeps ONE accumulator, so lora_up is stored divided by alpha * wcscales; a scale the quotient cannot survive
+    (zero / denormal / non-finite channel, fp16 overflow) is refused at repack time instead of producing inf / NaN outputs"""
+    g = torch.Generator().manual_seed(3)
+    N, R = 256, 32
+    lu = (0.05 * torch.randn(N, R, generator=g)).to(dtype)
+    packed = F.pack_lowrank(lu, down=False).cuda()
+    small = torch.full((N,), 2.0e-4)                       # a realistic NVFP4 weight-tensor scale: quotients ~ 1e2 .. 1e3, fine in fp16
+    got = rp.lora_up(packed, small.cuda(), cache=False).cpu()
+    assert torch.isfinite(got.float()).all()
+    assert torch.allclose(got.float(), L.lora_up_blocks(lu, small).float(), rtol=2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10, atol=0)
+    zero = small.clone()
+    zero[17] = 0.0
+    with pytest.raises(RuntimeError, match="channel 17"):
+        rp.lora_up(packed, zero.cuda(), cache=False)
+    nan = small.clone()
+    nan[200] = float("nan")
+    with pytest.raises(RuntimeError, match="channel 200"):
+        rp.lora_up(packed, nan.cuda(), cache=False)
+    tiny = torch.full((N,), 1.0e-8)                        # 0.05 / 1e-8 = 5e6: beyond fp16 (65504), representable in bf16
+    if dtype == torch.float16:
+        with pytest.raises(RuntimeError, match="overflows"):
+            rp.lora_up(packed, tiny.cuda(), cache=False)
+    else:
+        assert torch.isfinite(rp.lora_up(packed, tiny.cuda(), cache=False).float()).all()
+
+
+@pytest.mark.parametrize("hT", [torch.float16, torch.bfloat16])
+def test_nvfp4_layer_with_small_weight_tensor_scale_matches_the_oracle(hT):
+    """fp16 + alpha ~ 1e-3 (what real NVFP4 checkpoints carry): lora_up / (alpha * wcscales) stays in range and the output matches"""
+    from oracle import svdq as O
+
+    layer = O.make_synthetic_layer(256, 384, 32, fp4=True, hT=hT, seed=311)
+    assert layer.alpha < 5e-3
+    m, _ = _module(layer, precision="nvfp4")
+    x = O.make_activations(300, 384, hT, seed=312, smooth=layer.smooth)
+    y = m(x.cuda().view(1, 300, 384)).view(300, 256)
+    torch.cuda.synchronize()
+    assert O.rel_fro(y.cpu(), O.svdq_linear_forward(layer, x, mode="ref")) <= (1e-2 if hT == torch.bfloat16 else 3e-3)
+
+
 def _module(layer, precision="int4", act_unsigned=False, device="cuda"):
     from gpu_util import ref_layout_params
     from nunchaku_b200.models.linear import SVDQW4A4Linear

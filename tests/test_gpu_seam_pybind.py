@@ -56,6 +56,40 @@ def test_pybind_ops_match_python_operator_layer(C, fp4, hT):
     assert O.rel_fro(out.cpu(), y_ref) <= 1.5e-2
 
 
+def test_pybind_cache_survives_address_reuse_and_in_place_updates(C):
+    """torch's allocator hands a freed weight's device address to the next weight of the same size, and LoRA merges / load_state_dict
+    update parameters in place: the converted-weight cache behind `_C.ops` is keyed on the live storage + version counter, not on the
+    address alone (csrc/seam/pybind_ops.cpp)"""
+    N, K, R, M, Mp = 256, 256, 32, 256, 256
+    hT = torch.bfloat16
+    outs = []
+    for seed in (601, 602):
+        layer = O.make_synthetic_layer(N, K, R, fp4=True, hT=hT, seed=seed)
+        p = ref_layout_params(layer)
+        x = O.make_activations(M, K, hT, seed=77, smooth=layer.smooth).cuda()
+        act = torch.empty(Mp, K // 2, dtype=torch.uint8, device="cuda")
+        asc = torch.empty(K // 16, Mp, dtype=torch.float8_e4m3fn, device="cuda")
+        la = torch.empty(Mp, R, dtype=torch.float32, device="cuda")
+
+        def run():
+            C.ops.quantize_w4a4_act_fuse_lora(x, act, asc, p["proj_down"], la, p["smooth"], False, True)
+            out = torch.empty(M, N, dtype=hT, device="cuda")
+            C.ops.gemm_w4a4(act, p["qweight"], out, None, asc, p["wscales"], None, None, la, p["proj_up"], None, None, None, None, None, p["bias"], None,
+                            None, None, False, [1.0, 1.0], False, True, float(layer.alpha), p["wcscales"], None, None, None, 0)
+            return out
+
+        out = run()
+        assert O.rel_fro(out.cpu(), O.svdq_linear_forward(layer, x.cpu(), mode="ref")) <= 1.5e-2, seed
+        ptrs = {k: v.data_ptr() for k, v in p.items() if v is not None}
+        outs.append(out.clone())
+        # in-place update of a parameter (same storage, same address): the next call must see it
+        p["bias"].add_(1.0)
+        out_b = run()
+        assert O.rel_fro((out_b.float() - out.float()).cpu(), torch.ones(M, N)) <= 2e-2
+        del p, layer, out, out_b   # free: the next iteration's parameters are likely to land on the same addresses
+    assert not torch.equal(outs[0], outs[1]) and ptrs
+
+
 def test_pybind_utils_and_out_of_scope_entries(C):
     C.utils.set_log_level("info")
     C.utils.disable_memory_auto_release()

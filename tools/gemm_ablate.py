@@ -17,7 +17,7 @@ import torch  # noqa: E402
 
 from op_sweep import make_layer, time_fn  # noqa: E402
 
-CASES = [(0, "full kernel"), (1024, "3-stage TMA ring (valid)"), (2048, "2-stage TMA ring (valid)"), (512, "low-rank conversion at tile start (valid)"), (128, "no low-rank"), (16, "no SF copies"), (8, "no epilogue math/stores"), (4, "no MMAs (loads + copies + epilogue)"),
+CASES = [(0, "full kernel"), (8192, "cluster-scope acquire on the MMA warp's waits (valid)"), (1024, "3-stage TMA ring (valid)"), (2048, "2-stage TMA ring (valid)"), (512, "low-rank conversion at tile start (valid)"), (128, "no low-rank"), (16, "no SF copies"), (8, "no epilogue math/stores"), (4, "no MMAs (loads + copies + epilogue)"),
          (96, "no loads, no operand waits (MMA + copies + epilogue)"), (96 + 16, "no loads, no copies (MMA + epilogue)"),
          (96 + 16 + 128, "no loads, no copies, no low-rank"), (96 + 16 + 128 + 8, "MMA issue only"), (4 + 16 + 8 + 128, "load pipeline only")]
 
@@ -45,7 +45,7 @@ def main():
     rows = []
     for bn in [int(b) for b in args.bn.split(",")]:
         G.BLOCK_N_OVERRIDE = bn
-        for bits, name in ((CASES[:4] if args.valid_only else CASES) if bn >= 1024 else CASES[:1]):   # older kernels: control measurement on the same box
+        for bits, name in ((CASES[:5] if args.valid_only else CASES) if bn >= 1024 else CASES[:1]):   # older kernels: control measurement on the same box
             libc.setenv(b"NB200_GEMM_DEBUG", str(bits).encode(), 1)
             print(f"bn={bn:5d} bits={bits:4d} ...", end=" ", flush=True)
             t, tmin = time_fn(lambda: m.forward_quant(q, s, la, out), args.iters, flush)

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--K", type=int, default=3072)
     ap.add_argument("--N", type=int, default=3072)
     ap.add_argument("--bn", default="256,512,1024,2048")
+    ap.add_argument("--timeline", action="store_true", help="print block 0's MMA-thread timeline (cluster kernel)")
     ap.add_argument("--fused", action="store_true", help="profile the fc1 -> GELU -> quantise-for-fc2 epilogue (EPI_QUANT)")
     args = ap.parse_args()
     from nunchaku_b200.ops import gemm as G
@@ -54,7 +55,7 @@ def main():
             G.BLOCK_N_OVERRIDE = bn
             for _ in range(3):
                 run()
-            prof = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+            prof = torch.zeros(148 + 12 + 16, 16, dtype=torch.int64, device=dev)
             G.PROF_BUFFER = prof
             torch.cuda.synchronize()
             torch.cuda._sleep(int(2e7))
@@ -66,9 +67,24 @@ def main():
             G.PROF_BUFFER = None
             G.BLOCK_N_OVERRIDE = 0
             us = e0.elapsed_time(e1) * 1e3
-            pr = prof.cpu().double()
+            if args.timeline:
+                tl = prof.cpu()[160:].reshape(-1)
+                tl = tl[tl != 0]
+                names = {1: "tile begin", 2: "tmem_empty ok", 3: "operands ok", 4: "stage issued"}
+                prev = 0
+                out = []
+                for v in tl.tolist():
+                    t, tag = v >> 4, v & 15
+                    out.append(f"{names.get(tag, tag)}@{t}(+{t - prev})")
+                    prev = t
+                print("   timeline:", "  ".join(out))
+            pr = prof.cpu()[:148].double()
             used = pr[:, 10] > 0 if bn < 512 else pr[:, 5] > 0
             print(f"== {prec} M={args.M} K={args.K} N={args.N} bn={bn}: {us:.1f} us  ({2*args.M*args.K*args.N/us/1e6:.0f} TFLOP/s)  CTAs with data {int(used.sum())}")
+            ns = pr[:, 14]
+            if (ns > 0).any():
+                sel = ns > 0
+                print(f"   effective SM clock inside the kernel: {(pr[sel, 9] / ns[sel]).mean().item() * 1e3:.0f} MHz   CTA wall time mean {ns[sel].mean().item() / 1e3:.1f} us max {ns[sel].max().item() / 1e3:.1f} us")
             for k, name in SLOTS.items():
                 col = pr[:, k]
                 nz = col[col > 0]
