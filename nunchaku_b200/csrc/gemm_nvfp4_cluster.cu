@@ -79,18 +79,18 @@ struct alignas(1024) SmemC {
     alignas(1024) uint8_t b[kStages][kBBytes];
     alignas(128) uint8_t sa[kStages][kSaBytes];
     alignas(128) uint8_t sb[kStages][kSbBytes];
-    alignas(1024) uint8_t lora_a[BM * kLoraChunk * 2];
+    alignas(1024) uint8_t lora_a[2][BM * kLoraChunk * 2];   // low-rank activations of tile it in buffer it & 1 (converted one tile ahead)
     alignas(1024) uint8_t lora_b[BH * kLoraChunk * 2];
     alignas(1024) uint8_t out_stage[2][BM * 128];
-    float bias[BN];
-    float cscale[BN];
+    alignas(16) float bias[2][BN];     // tile it in buffer it & 1: fetched one tile ahead, read back as float4 broadcasts
+    alignas(16) float cscale[2][BN];
     float normw[256];          // EPI_ROPE: RMSNorm weights (q | k)
     uint64_t full[kStages];    // pair leader: all TMA bytes of the pair's stage
     uint64_t empty[kStages];   // every CTA: kPairs multicast commits
     uint64_t tmem_full;        // multicast commit to the pair
     uint64_t tmem_empty;       // pair leader: 2 x 8 epilogue-warp arrivals
     uint64_t lora_b_full;      // pair leader: TMA bytes of both halves
-    uint64_t lora_a_full;      // pair leader: 2 x 8 epilogue-warp arrivals
+    uint64_t lora_a_full[2];   // pair leader: 2 x 8 epilogue-warp arrivals, one barrier per lora_a buffer
     uint64_t lora_empty;       // multicast commit to the pair
     uint32_t tmem_base;
 };
@@ -166,6 +166,9 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
     // Tried and dropped (r02, tools/gemm_ablate.py on one box): scale factors on their own mbarrier, loaded first and copied to TMEM one
     // stage ahead -- 12 % SLOWER on 4096x3072x3072, 26 % slower on K = 12288 (34.8 -> 39.0 us, 86 -> 108 us)
     const int lora_chunks = (p.has_lora && !(p.debug & 128)) ? p.Rp / kLoraChunk : 0;
+    // one 32-rank chunk: the low-rank activations of tile it + 1 are converted while tile it is still in its main loop, into the other
+    // lora_a buffer (with more chunks the single buffer 0 is recycled chunk by chunk inside a tile: lora_empty hand-shake)
+    const bool lora_ahead = !(p.debug & 512) && lora_chunks <= 1;
     const uint32_t ring = (p.debug & 2048) ? 2 : ((p.debug & 1024) ? 3 : kStages);   // ablation: shallower TMA ring (results stay valid)
     constexpr uint16_t kMaskAll = (1u << kCtas) - 1;
     const uint16_t mask_pair = static_cast<uint16_t>(3u << (2 * pi));
@@ -187,7 +190,8 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
         mbar_init(&s.tmem_full, 1);
         mbar_init(&s.tmem_empty, 2 * kEpiWarps);
         mbar_init(&s.lora_b_full, 1);
-        mbar_init(&s.lora_a_full, 2 * kEpiWarps);
+        mbar_init(&s.lora_a_full[0], 2 * kEpiWarps);
+        mbar_init(&s.lora_a_full[1], 2 * kEpiWarps);
         mbar_init(&s.lora_empty, 1);
         fence_mbar_init();
     }
@@ -269,15 +273,16 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
         const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(s.a[0])), bdesc0 = make_sw128_kmajor_desc(smem_u32(s.b[0]));
         const uint64_t sadesc0 = make_smem_desc(smem_u32(s.sa[0]), 0, 128, kLayoutNoSwizzle);
         const uint64_t sbdesc0 = make_smem_desc(smem_u32(s.sb[0]), 0, 128, kLayoutNoSwizzle);
-        const uint64_t ladesc0 = make_smem_desc(smem_u32(s.lora_a), 128, 512, kLayoutNoSwizzle);
+        const uint64_t ladesc0 = make_smem_desc(smem_u32(s.lora_a[0]), 128, 512, kLayoutNoSwizzle);
+        constexpr uint64_t kLoraABufDesc = (BM * kLoraChunk * 2) >> 4;
+        uint32_t it = 0;
         const uint64_t lbdesc0 = make_smem_desc(smem_u32(s.lora_b), 128, 512, kLayoutNoSwizzle);
         const uint32_t tmem_d = tmem_base;
         // NB200_GEMM_DEBUG=4096 + a prof buffer: timeline of block 0's issuing lane (tools/gemm_prof.py --timeline), otherwise untouched
         long long *tl = ((p.debug & 4096) && p.prof != nullptr && blockIdx.x == 0) ? p.prof + 160 * 16 : nullptr;
         int tli = 0;
-        const long long t_tl0 = clock64();
         auto mark = [&](int tag) {
-            if (tl != nullptr && tli < 255) tl[tli++] = ((clock64() - t_tl0) << 4) | tag;
+            if (tl != nullptr && tli < 255) tl[tli++] = ((clock64() - t_kernel0) << 4) | tag;   // same origin as the epilogue timeline
         };
         const bool cluster_acq = (p.debug & 8192) != 0;
         for (int ct = cluster_id; ct < p.num_ct; ct += num_clusters) {
@@ -326,12 +331,13 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
             }
             for (int c = 0; c < lora_chunks; c++) {
                 mbar_wait(&s.lora_b_full, lora_phase);
-                if (cluster_acq) mbar_wait_cluster(&s.lora_a_full, lora_phase);
-                else mbar_wait(&s.lora_a_full, lora_phase);
+                const uint32_t lb = lora_ahead ? (it & 1) : 0, lph = lora_ahead ? ((it >> 1) & 1) : lora_phase;
+                if (cluster_acq) mbar_wait_cluster(&s.lora_a_full[lb], lph);
+                else mbar_wait(&s.lora_a_full[lb], lph);
                 tc_fence_after_sync();
                 if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kLoraChunk / 16; j++) tc_mma_f16_cg2(tmem_d, ladesc0 + 16 * j, lbdesc0 + 16 * j, idesc_lora, 1);
+                    for (int j = 0; j < kLoraChunk / 16; j++) tc_mma_f16_cg2(tmem_d, ladesc0 + lb * kLoraABufDesc + 16 * j, lbdesc0 + 16 * j, idesc_lora, 1);
                     tc_commit_cg2(&s.lora_empty, mask_pair);
                 }
                 __syncwarp();
@@ -340,6 +346,7 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
             if (elect_one()) tc_commit_cg2(&s.tmem_full, mask_pair);
             __syncwarp();
             acc_phase ^= 1;
+            it++;
         }
     } else if (warp == 1) {
         // ============ MMA issuer, instrumented path (profiling counters / ablation bits): one thread, clock reads around the waits =======
@@ -358,7 +365,8 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
             auto mark = [&](int tag) {
                 if (tl && tli < 255) tl[tli++] = ((clock64() - t_mma0) << 4) | tag;
             };
-            for (int ct = cluster_id; ct < p.num_ct; ct += num_clusters) {
+            uint32_t it = 0;
+            for (int ct = cluster_id; ct < p.num_ct; ct += num_clusters, it++) {
                 mark(1);
                 if (lean) mbar_wait_cluster(&s.tmem_empty, acc_phase ^ 1);
                 else NB200_TIMED(t_tmem_empty, mbar_wait_cluster(&s.tmem_empty, acc_phase ^ 1));
@@ -389,15 +397,16 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                     st.advance();
                 }
                 for (int c = 0; c < lora_chunks; c++) {
+                    const uint32_t lb = lora_ahead ? (it & 1) : 0, lph = lora_ahead ? ((it >> 1) & 1) : lora_phase;
                     if (lean) {
                         mbar_wait_cluster(&s.lora_b_full, lora_phase);
-                        mbar_wait_cluster(&s.lora_a_full, lora_phase);
+                        mbar_wait_cluster(&s.lora_a_full[lb], lph);
                     } else {
                         NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_b_full, lora_phase));
-                        NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_a_full, lora_phase));
+                        NB200_TIMED(t_lora, mbar_wait_cluster(&s.lora_a_full[lb], lph));
                     }
                     tc_fence_after_sync();
-                    const uint32_t a_addr = smem_u32(s.lora_a), b_addr = smem_u32(s.lora_b);
+                    const uint32_t a_addr = smem_u32(s.lora_a[lb]), b_addr = smem_u32(s.lora_b);
 #pragma unroll
                     for (int j = 0; j < kLoraChunk / 16; j++)
                         tc_mma_f16_cg2(tmem_d, make_smem_desc(a_addr + j * 256, 128, 512, kLayoutNoSwizzle),
@@ -428,7 +437,7 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
         long long t_tmem_full = 0, t_pre = 0;
         const long long t_epi0 = clock64();
         const uint32_t leader_rank = rank & ~1u;
-        const uint32_t lora_a_full_leader = mapa(smem_u32(&s.lora_a_full), leader_rank);
+        const uint32_t lora_a_full_leader[2] = {mapa(smem_u32(&s.lora_a_full[0]), leader_rank), mapa(smem_u32(&s.lora_a_full[1]), leader_rank)};
         const uint32_t tmem_empty_leader = mapa(smem_u32(&s.tmem_empty), leader_rank);
         if constexpr (EPI == EPI_ROPE) {
             for (int i = eta; i < 256; i += kEpiThreads)
@@ -439,11 +448,17 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
         // thread, group h converts 16 of the 32 ranks of a chunk.  Called ONE TILE AHEAD (right after this tile's accumulator has
         // been pulled into registers): the MMA warp reaches the low-rank MMAs of tile i+1 while these warps are still busy with the
         // math and stores of tile i, and must not wait for them.
-        auto convert_lora = [&](const int m0_) {
+        // NB200_GEMM_DEBUG=4096 + a prof buffer of >= 192 rows: timeline of block 0's first epilogue thread (tools/gemm_prof.py --timeline)
+        long long *etl = ((p.debug & 4096) && p.prof != nullptr && blockIdx.x == 0 && eta == 0) ? p.prof + 176 * 16 : nullptr;
+        int etli = 0;
+        auto emark = [&](int tag) {
+            if (etl != nullptr && etli < 255) etl[etli++] = ((clock64() - t_kernel0) << 4) | tag;
+        };
+        auto convert_lora = [&](const int m0_, const uint32_t buf) {
             for (int c = 0; c < lora_chunks; c++) {
-                mbar_wait(&s.lora_empty, lora_phase ^ 1);
+                if (!lora_ahead) mbar_wait(&s.lora_empty, lora_phase ^ 1);   // (ahead: the other buffer's last reader finished a tile ago)
                 const float *src = p.lora_act + static_cast<size_t>(m0_ + row) * p.R + c * kLoraChunk;
-                uint8_t *dst = s.lora_a + (row >> 3) * 512 + (row & 7) * 16;
+                uint8_t *dst = s.lora_a[buf] + (row >> 3) * 512 + (row & 7) * 16;
 #pragma unroll
                 for (int oo = 0; oo < 4 / H; oo++) {
                     const int o = h * (4 / H) + oo;
@@ -466,28 +481,42 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(lora_a_full_leader);
+                if (lane == 0) mbar_arrive_remote(lora_a_full_leader[buf]);
                 lora_phase ^= 1;
             }
         };
-        // (single 32-rank chunk only: with more chunks the one lora_a buffer is released chunk by chunk in the middle of the NEXT tile)
-        const bool lora_ahead = !(p.debug & 512) && lora_chunks <= 1;
-        if (lora_ahead && cluster_id < p.num_ct) convert_lora((cluster_id / p.nct_n) * 2 * BM + q * BM);
-        for (int ct = cluster_id; ct < p.num_ct; ct += num_clusters) {
-            const int mb2 = ct / p.nct_n, nb = (ct % p.nct_n) * kPairs + pi;
-            const int m0 = mb2 * 2 * BM + q * BM, n0 = nb * BN;
-            const long long t_tile0 = clock64();
-
-            named_bar_sync(1, kEpiThreads);
+        // bias / per-channel scale of one tile -> shared memory (thread eta owns column eta: a group only reads what its own threads wrote)
+        auto fetch_channel_vectors = [&](const int n0_, const uint32_t buf) {
             for (int i = eta; i < BN; i += kEpiThreads) {
-                s.bias[i] = p.bias != nullptr ? p.bias[n0 + i] : 0.f;
-                s.cscale[i] = p.cscale != nullptr ? p.cscale[n0 + i] : 1.f;
+                s.bias[buf][i] = p.bias != nullptr ? p.bias[n0_ + i] : 0.f;
+                s.cscale[buf][i] = p.cscale != nullptr ? p.cscale[n0_ + i] : 1.f;
             }
-            named_bar_sync(1, kEpiThreads);
-            if (!lora_ahead) convert_lora(m0);
+        };
+        auto tile_m0 = [&](const int ct_) { return (ct_ / p.nct_n) * 2 * BM + q * BM; };
+        auto tile_n0 = [&](const int ct_) { return ((ct_ % p.nct_n) * kPairs + pi) * BN; };
+        if (cluster_id < p.num_ct) {
+            fetch_channel_vectors(tile_n0(cluster_id), 0);
+            if (lora_ahead) convert_lora(tile_m0(cluster_id), 0);
+        }
+        uint32_t it = 0;
+        for (int ct = cluster_id; ct < p.num_ct; ct += num_clusters, it++) {
+            const int m0 = tile_m0(ct), n0 = tile_n0(ct);
+            const long long t_tile0 = clock64();
+            const float *bias_s = s.bias[it & 1], *cscale_s = s.cscale[it & 1];
+            // While this tile's MMAs are still running: everything the NEXT tile's epilogue (and its low-rank MMAs) will need.  The
+            // barrier orders the previous iteration's writes of this tile's vectors before their use below, and the previous tile's
+            // reads of the other buffer before its refill here.
+            named_bar_sync(2 + 2 * h, 128);
+            if (ct + num_clusters < p.num_ct) {
+                fetch_channel_vectors(tile_n0(ct + num_clusters), (it + 1) & 1);
+                if (lora_ahead) convert_lora(tile_m0(ct + num_clusters), (it + 1) & 1);
+            }
+            if (!lora_ahead) convert_lora(m0, 0);
 
             t_pre += clock64() - t_tile0;
+            emark(1);
             NB200_TIMED(t_tmem_full, mbar_wait(&s.tmem_full, acc_phase));
+            emark(2);
             acc_phase ^= 1;
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + h * 128;
@@ -500,8 +529,8 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
-            if (lora_ahead && ct + num_clusters < p.num_ct) convert_lora(((ct + num_clusters) / p.nct_n) * 2 * BM + q * BM);
+            if (lane == 0) mbar_arrive_remote(tmem_empty_leader);
+            emark(3);
             if (p.debug & 8) continue;
 
             // ---- EPI_ROPE: one 128-wide head per group
@@ -520,12 +549,16 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                     float sumsq = 0.f;
                     auto acc_sq = [&](const uint32_t(&v)[32], const int cbase) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float y0 = fmaf(__uint_as_float(v[i]), s.cscale[cbase + i], s.bias[cbase + i]);
-                            const float y1 = fmaf(__uint_as_float(v[i + 1]), s.cscale[cbase + i + 1], s.bias[cbase + i + 1]);
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 cs = *reinterpret_cast<const float4 *>(cscale_s + cbase + i), bs = *reinterpret_cast<const float4 *>(bias_s + cbase + i);
+                            const float y0 = fmaf(__uint_as_float(v[i]), cs.x, bs.x), y1 = fmaf(__uint_as_float(v[i + 1]), cs.y, bs.y);
+                            const float y2 = fmaf(__uint_as_float(v[i + 2]), cs.z, bs.z), y3 = fmaf(__uint_as_float(v[i + 3]), cs.w, bs.w);
                             const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));   // fpsum is hT (epilogues.cuh:327-341)
+                            const float2 r2 = Tr::to_float2(Tr::from_float2(make_float2(y2, y3)));
                             sumsq = fmaf(r.x, r.x, sumsq);
                             sumsq = fmaf(r.y, r.y, sumsq);
+                            sumsq = fmaf(r2.x, r2.x, sumsq);
+                            sumsq = fmaf(r2.y, r2.y, sumsq);
                         }
                     };
                     acc_sq(va, h * 128);
@@ -546,6 +579,7 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                 const int ch = h * 2 + cc;   // chunk inside the 256-wide tile
                 if (et == 0 && !pack_qkv) bulk_wait_group_read<0>();
                 if (!pack_qkv) named_bar_sync(2 + 2 * h, 128);
+                emark(5);
                 uint8_t *srow = s.out_stage[h] + row * 128;
                 [[maybe_unused]] __half *qkv_row = nullptr;
                 [[maybe_unused]] bool qkv_masked = false;
@@ -558,13 +592,17 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
 #pragma unroll
                 for (int c8 = 0; c8 < 8; c8++) {
                     uint32_t w[4];
+                    const float4 csA = *reinterpret_cast<const float4 *>(cscale_s + ch * 64 + c8 * 8), csB = *reinterpret_cast<const float4 *>(cscale_s + ch * 64 + c8 * 8 + 4);
+                    const float4 bsA = *reinterpret_cast<const float4 *>(bias_s + ch * 64 + c8 * 8), bsB = *reinterpret_cast<const float4 *>(bias_s + ch * 64 + c8 * 8 + 4);
+                    const float cs8[8] = {csA.x, csA.y, csA.z, csA.w, csB.x, csB.y, csB.z, csB.w};
+                    const float bs8[8] = {bsA.x, bsA.y, bsA.z, bsA.w, bsB.x, bsB.y, bsB.z, bsB.w};
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int col = c8 * 8 + 2 * i;
                         float y0 = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
                         float y1 = __uint_as_float(col + 1 < 32 ? v0[col + 1] : v1[col + 1 - 32]);
-                        y0 = fmaf(y0, s.cscale[ch * 64 + col], s.bias[ch * 64 + col]);
-                        y1 = fmaf(y1, s.cscale[ch * 64 + col + 1], s.bias[ch * 64 + col + 1]);
+                        y0 = fmaf(y0, cs8[2 * i], bs8[2 * i]);
+                        y1 = fmaf(y1, cs8[2 * i + 1], bs8[2 * i + 1]);
                         if constexpr (EPI == EPI_ROPE) {
                             if (do_rope) {
                                 const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));
@@ -610,8 +648,10 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                     *reinterpret_cast<uint4 *>(srow + ((c8 ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 if (pack_qkv) return;
+                emark(6);
                 fence_proxy_async_smem();
                 named_bar_sync(3 + 2 * h, 128);
+                emark(7);
                 if (et == 0) {
                     tma_store_2d(&tm_out, s.out_stage[h], n0 + ch * 64, m0);
                     bulk_commit_group();

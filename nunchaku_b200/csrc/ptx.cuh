@@ -269,6 +269,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// the same with the default (CTA-scope) release, as CUTLASS's ClusterBarrier::arrive(cta_id): enough when what the arrival publishes is
+// async-proxy state (a completed tcgen05.ld / wait::ld, shared memory already fenced with fence.proxy.async), and without the
+// cluster-scope fence that the release.cluster form drags in (MEMBAR stalls on the accumulator hand-off, r02 epilogue timeline)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // In a 2-CTA cluster the rank sits in bit 24 of a shared::cluster address: clearing it turns the
 // address of a local object into the address of the same object in the leader CTA.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;

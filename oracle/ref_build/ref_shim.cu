@@ -167,11 +167,13 @@ int nref_test_pack_qkv(const nref_tensor *input, const nref_tensor *out_q, const
     return guarded(stream, [&] { nunchaku::kernels::test_pack_qkv(wrap(input), wrap(out_q), wrap(out_k), wrap(out_v), num_tokens); });
 }
 
+#endif
+
+// (both builds: in the seam library `gemv_awq` is OUR definition, nunchaku_b200/csrc/seam/awq_b200.cpp)
 int nref_gemv_awq(const nref_tensor *x, const nref_tensor *qweight, const nref_tensor *scales, const nref_tensor *zeros, int m, int n, int k,
                   int group_size, const nref_tensor *out, void *stream) {
     return guarded(stream, [&] { copy_out(out, gemv_awq(wrap(x), wrap(qweight), wrap(scales), wrap(zeros), m, n, k, group_size)); });
 }
-#endif
 
 // ---- glue ----------------------------------------------------------------------------------
 // kind: 0 silu, 1 gelu_new   (Silu::forward / GELU::forward, src/activation.cpp:4-14)

@@ -55,7 +55,7 @@ def main():
             G.BLOCK_N_OVERRIDE = bn
             for _ in range(3):
                 run()
-            prof = torch.zeros(148 + 12 + 16, 16, dtype=torch.int64, device=dev)
+            prof = torch.zeros(148 + 12 + 16 + 16, 16, dtype=torch.int64, device=dev)
             G.PROF_BUFFER = prof
             torch.cuda.synchronize()
             torch.cuda._sleep(int(2e7))
@@ -68,7 +68,7 @@ def main():
             G.BLOCK_N_OVERRIDE = 0
             us = e0.elapsed_time(e1) * 1e3
             if args.timeline:
-                tl = prof.cpu()[160:].reshape(-1)
+                tl = prof.cpu()[160:176].reshape(-1)
                 tl = tl[tl != 0]
                 names = {1: "tile begin", 2: "tmem_empty ok", 3: "operands ok", 4: "stage issued"}
                 prev = 0
@@ -78,6 +78,17 @@ def main():
                     out.append(f"{names.get(tag, tag)}@{t}(+{t - prev})")
                     prev = t
                 print("   timeline:", "  ".join(out))
+                etl = prof.cpu()[176:192].reshape(-1)
+                etl = etl[etl != 0]
+                enames = {1: "pre-tile done", 2: "tmem_full ok", 3: "accumulator in registers, tmem_empty sent", 4: "next tile's low-rank converted", 5: "staging free",
+                          6: "chunk computed", 7: "chunk handed to TMA"}
+                prev = 0
+                out = []
+                for v in etl.tolist():
+                    t, tag = v >> 4, v & 15
+                    out.append(f"{enames.get(tag, tag)}@{t}(+{t - prev})")
+                    prev = t
+                print("   epilogue timeline:", "  ".join(out))
             pr = prof.cpu()[:148].double()
             used = pr[:, 10] > 0 if bn < 512 else pr[:, 5] > 0
             print(f"== {prec} M={args.M} K={args.K} N={args.N} bn={bn}: {us:.1f} us  ({2*args.M*args.K*args.N/us/1e6:.0f} TFLOP/s)  CTAs with data {int(used.sum())}")
