@@ -1,0 +1,311 @@
+// Scaled-dot-product attention of the FLUX blocks on tcgen05.
+//
+// Replaces nunchaku::kernels::attention_fp16 (src/kernels/zgemm/attention.cu:10-94, kernel attention.cuh:420-703; Python
+// NunchakuFP16AttnProcessor, nunchaku/models/attention_processors/flux.py): q / k / v fp16 [B, H, T, 128] as the QKV projection's PackQKV
+// epilogue writes them (row-major inside a head: OUR layout -- the reference stores its own mma.sync fragment order there), pad rows of K
+// are NaN and act as the mask (scores NaN -> -inf, attention.cuh:192-221), o hT [B, Tq, H * 128], softmax in base 2 with
+// scale * log2(e) folded in (attention.cu:48-49), non-causal.
+//
+// One CTA per (128 query rows, head).  Flash-attention forward with both GEMMs on the 5th-generation tensor cores:
+//   S = Q K^T   : tcgen05.mma kind::f16, M = 128, N = 128 keys, K = 128 (8 instructions); Q and K tiles are K-major SW128 TMA boxes;
+//                 the S accumulator is double buffered in TMEM so that S(j+1) runs under the softmax of tile j
+//   softmax     : 128 threads, thread = query row = TMEM lane (no shuffles): tcgen05.ld of the row's 128 scores, running max / sum in
+//                 fp32, ex2.approx, P rounded to fp16 into shared memory in the K-major SW128 operand layout
+//   O += P V    : A = P (shared memory), B = V as an MN-major SW128 operand (V is [keys, d] row-major: keys are the K dimension, d
+//                 is contiguous -- no transpose anywhere), fp32 accumulator in TMEM; when a row's running max moved, O is rescaled in
+//                 TMEM (tcgen05.ld / st) before the next P V is issued
+//   epilogue    : O * rcp(l) -> hT -> global
+// The reference accumulates Q K^T and P V in fp16 per 32-key tile (mma.sync f16 accumulate, attention.cuh:185-260,341-366); fp32
+// accumulation here is strictly more accurate, so parity is to fp16 noise (tests/test_gpu_attention.py: vs fp64 softmax attention, vs
+// the reference kernel live on the same GPU).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace nb200 {
+namespace {
+
+using namespace ptx;
+
+constexpr int kD = 128;            // head dimension
+constexpr int kBM = 128;           // query rows per CTA
+constexpr int kBN = 128;           // keys per tile
+constexpr int kSlab = kBM * 128;   // one [128 rows x 128 B] SW128 box = 64 fp16 columns
+constexpr int kTile = 2 * kSlab;   // a 128 x 128 fp16 tile: 32 KB
+constexpr int kKvStages = 2;
+constexpr int kThreadsAttn = 256;  // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 softmax / correction / epilogue
+
+struct alignas(1024) SmemA {
+    alignas(1024) uint8_t q[kTile];
+    alignas(1024) uint8_t k[kKvStages][kTile];
+    alignas(1024) uint8_t v[kKvStages][kTile];
+    alignas(1024) uint8_t p[kTile];
+    uint64_t q_full;
+    uint64_t k_full[kKvStages], k_empty[kKvStages];
+    uint64_t v_full[kKvStages], v_empty[kKvStages];
+    uint64_t s_full[2], s_empty[2];
+    uint64_t p_full, pv_done;
+    uint32_t tmem_base;
+};
+static_assert(sizeof(SmemA) + 1024 <= 232448, "shared memory budget");
+
+struct AttnParams {
+    void *o;
+    int heads, tokens_q, tokens_kv;
+    float scale_log2;   // scale * log2(e)
+    int out_bf16;
+};
+
+// MN-major SW128 operand (V: [keys][64 d] boxes, two boxes for d = 128): start address + 16 keys per instruction;
+// LBO = distance between the two 64-wide d blocks, SBO = distance between groups of 8 keys
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) { return make_smem_desc(smem_addr, kSlab, 1024, kLayoutSw128); }
+
+__global__ void __launch_bounds__(kThreadsAttn, 1)
+attention_fp16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                      const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    SmemA &s = *reinterpret_cast<SmemA *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+    const int n_tiles = p.tokens_kv / kBN;
+    const int q_row0 = (batch * p.heads + head) * p.tokens_q + qb * kBM;    // row in the [B * H * Tq, 128] view
+    const int kv_row0 = (batch * p.heads + head) * p.tokens_kv;
+
+    if (warp == 0 && elect_one()) {
+        prefetch_tensormap(&tm_q);
+        prefetch_tensormap(&tm_k);
+        prefetch_tensormap(&tm_v);
+        mbar_init(&s.q_full, 1);
+        for (int i = 0; i < kKvStages; i++) {
+            mbar_init(&s.k_full[i], 1);
+            mbar_init(&s.k_empty[i], 1);
+            mbar_init(&s.v_full[i], 1);
+            mbar_init(&s.v_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&s.s_full[i], 1);
+            mbar_init(&s.s_empty[i], 4);
+        }
+        mbar_init(&s.p_full, 4);
+        mbar_init(&s.pv_done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<512>(&s.tmem_base);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = s.tmem_base;
+    const uint32_t tmem_s[2] = {tmem_base, tmem_base + 128};
+    const uint32_t tmem_o = tmem_base + 256;
+    griddep_launch_dependents();
+    griddep_wait();
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (elect_one()) {
+            mbar_expect_tx(&s.q_full, kTile);
+            tma_load_2d(s.q, &tm_q, &s.q_full, 0, q_row0);
+            tma_load_2d(s.q + kSlab, &tm_q, &s.q_full, 64, q_row0);
+            for (int j = 0; j < n_tiles; j++) {
+                const int st = j % kKvStages;
+                const uint32_t ph = (j / kKvStages) & 1;
+                mbar_wait(&s.k_empty[st], ph ^ 1);
+                mbar_expect_tx(&s.k_full[st], kTile);
+                tma_load_2d(s.k[st], &tm_k, &s.k_full[st], 0, kv_row0 + j * kBN);
+                tma_load_2d(s.k[st] + kSlab, &tm_k, &s.k_full[st], 64, kv_row0 + j * kBN);
+                mbar_wait(&s.v_empty[st], ph ^ 1);
+                mbar_expect_tx(&s.v_full[st], kTile);
+                tma_load_2d(s.v[st], &tm_v, &s.v_full[st], 0, kv_row0 + j * kBN);
+                tma_load_2d(s.v[st] + kSlab, &tm_v, &s.v_full[st], 64, kv_row0 + j * kBN);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (elect_one()) {
+            constexpr uint32_t idesc_qk = make_idesc_f16(false, kBM, kBN);
+            constexpr uint32_t idesc_pv = make_idesc_f16(false, kBM, kD) | (1u << 16);   // B (= V) is MN-major
+            const uint32_t q_addr = smem_u32(s.q), p_addr = smem_u32(s.p);
+            auto issue_s = [&](int j) {   // S(j) = Q K_j^T into S buffer j % 2
+                const int st = j % kKvStages, b = j & 1;
+                mbar_wait(&s.k_full[st], (j / kKvStages) & 1);
+                mbar_wait(&s.s_empty[b], ((j >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t k_addr = smem_u32(s.k[st]);
+#pragma unroll
+                for (int ks = 0; ks < kD / 16; ks++) {
+                    const uint32_t off = (ks >> 2) * kSlab + (ks & 3) * 32;
+                    tc_mma_f16(tmem_s[b], make_sw128_kmajor_desc(q_addr + off), make_sw128_kmajor_desc(k_addr + off), idesc_qk, ks != 0);
+                }
+                tc_commit(&s.k_empty[st]);
+                tc_commit(&s.s_full[b]);
+            };
+            mbar_wait(&s.q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < n_tiles; j++) {
+                if (j + 1 < n_tiles) issue_s(j + 1);
+                const int st = j % kKvStages;
+                mbar_wait(&s.p_full, j & 1);
+                mbar_wait(&s.v_full[st], (j / kKvStages) & 1);
+                tc_fence_after_sync();
+                const uint32_t v_addr = smem_u32(s.v[st]);
+#pragma unroll
+                for (int ks = 0; ks < kBN / 16; ks++) {
+                    const uint32_t a_off = (ks >> 2) * kSlab + (ks & 3) * 32;   // P: K-major, keys contiguous
+                    const uint32_t b_off = ks * 16 * 128;                       // V: 16 key rows of 128 B further
+                    tc_mma_f16(tmem_o, make_sw128_kmajor_desc(p_addr + a_off), make_sw128_mnmajor_desc(v_addr + b_off), idesc_pv, (j | ks) != 0);
+                }
+                tc_commit(&s.v_empty[st]);
+                tc_commit(&s.pv_done);
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================ softmax / correction / epilogue: thread = query row ==============================
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+        const float scale = p.scale_log2;
+        float m_run = -INFINITY, l_run = 0.f;
+        const uint32_t p_row = smem_u32(s.p) + row * 128;
+        for (int j = 0; j < n_tiles; j++) {
+            const int b = j & 1;
+            mbar_wait(&s.s_full[b], (j >> 1) & 1);
+            tc_fence_after_sync();
+            uint32_t sv[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; c++) tmem_ld_32x32b_x32(tmem_s[b] + lane_base + c * 32, sv[c]);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.s_empty[b]);
+            // running max (NaN scores = masked keys: fmaxf drops the NaN operand, attention.cuh:192-221)
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+            const float m_new = fmaxf(m_run, mx * scale);
+            const float alpha = ex2_approx_ftz(m_run - m_new);   // first tile: ex2(-inf) = 0
+            // p = 2^(s * scale - m_new); masked (NaN) scores -> 0
+            float sum = 0.f;
+            uint32_t pk[4][16];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float s0 = fmaxf(__uint_as_float(sv[c][i]), -INFINITY), s1 = fmaxf(__uint_as_float(sv[c][i + 1]), -INFINITY);
+                    const float e0 = ex2_approx_ftz(fmaf(s0, scale, -m_new)), e1 = ex2_approx_ftz(fmaf(s1, scale, -m_new));
+                    sum += e0 + e1;
+                    const __half2 h = __floats2half2_rn(e0, e1);
+                    pk[c][i >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+                }
+            l_run = fmaf(l_run, alpha, sum);
+            m_run = m_new;
+            // P V of the previous tile must be done before P is overwritten and before O is touched
+            if (j > 0) {
+                mbar_wait(&s.pv_done, (j - 1) & 1);
+                tc_fence_after_sync();
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {   // some row of this warp moved its maximum: rescale the warp's 32 rows of O
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t ov[32];
+                        tmem_ld_32x32b_x32(tmem_o + lane_base + c * 32, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                        tmem_st_32x32b_x32(tmem_o + lane_base + c * 32, ov);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            // P -> shared memory: [128 rows][2 slabs of 64 keys], 16-byte chunks XOR-swizzled by the row (SW128 K-major operand layout)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int chunk = (c & 1) * 4 + u;   // 16-byte chunk inside the slab's 128-byte row
+                    const uint32_t addr = p_row + (c >> 1) * kSlab + ((chunk ^ (row & 7)) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c][4 * u]), "r"(pk[c][4 * u + 1]), "r"(pk[c][4 * u + 2]),
+                                 "r"(pk[c][4 * u + 3])
+                                 : "memory");
+                }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.p_full);
+        }
+        // ---- epilogue: O / l -> hT -> o[batch, q, head * 128 + d]
+        mbar_wait(&s.pv_done, (n_tiles - 1) & 1);
+        tc_fence_after_sync();
+        const float inv = rcp_approx_ftz(l_run);
+        const size_t orow = (static_cast<size_t>(batch) * p.tokens_q + qb * kBM + row) * (static_cast<size_t>(p.heads) * kD) + static_cast<size_t>(head) * kD;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(tmem_o + lane_base + c * 32, ov);
+            tmem_ld_wait();
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const float a = __uint_as_float(ov[i]) * inv, bb = __uint_as_float(ov[i + 1]) * inv;
+                if (p.out_bf16) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(a, bb);
+                    w[i >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+                } else {
+                    const __half2 h = __floats2half2_rn(a, bb);
+                    w[i >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+                }
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(static_cast<uint16_t *>(p.o) + orow + c * 32);
+#pragma unroll
+            for (int u = 0; u < 4; u++) dst[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+        }
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace
+}  // namespace nb200
+
+// q / k / v: fp16 [batch, heads, tokens, 128] contiguous, row-major inside a head (the PackQKV epilogue's layout); o: fp16 / bf16
+// [batch, tokens_q, heads * 128].  tokens_q, tokens_kv multiples of 128.  scale: the softmax scale (1 / sqrt(128) for FLUX); the kernel works in
+// base 2 like the reference (attention.cu:48-49).
+extern "C" __attribute__((visibility("default"))) int nb200_attention_fp16(const void *q, const void *k, const void *v, void *o, int out_dtype, int batch,
+                                                                            int heads, int tokens_q, int tokens_kv, float scale, void *stream_) {
+    using namespace nb200;
+    reset_launch_count();
+    NB200_REQUIRE(q && k && v && o, "NULL tensor");
+    NB200_REQUIRE(batch > 0 && heads > 0, "batch / heads must be positive");
+    NB200_REQUIRE(tokens_q > 0 && tokens_q % kBM == 0, "tokens_q must be a positive multiple of 128 (attention.cu:51)");
+    NB200_REQUIRE(tokens_kv > 0 && tokens_kv % kBN == 0, "tokens_kv must be a positive multiple of 128");
+    NB200_REQUIRE(out_dtype == NB200_FP16 || out_dtype == NB200_BF16, "o must be fp16 or bf16");
+    NB200_REQUIRE(static_cast<long long>(batch) * heads * tokens_q < (1ll << 31) && static_cast<long long>(batch) * heads * tokens_kv < (1ll << 31), "too many rows");
+    if (int rc = nb200_check_device()) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CUtensorMap tm_q, tm_k, tm_v;
+    const uint64_t rows_q = static_cast<uint64_t>(batch) * heads * tokens_q, rows_kv = static_cast<uint64_t>(batch) * heads * tokens_kv;
+    int rc = make_map_2d(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, q, kD, rows_q, kD * 2, 64, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&tm_k, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, k, kD, rows_kv, kD * 2, 64, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map_2d(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, v, kD, rows_kv, kD * 2, 64, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    AttnParams p;
+    p.o = o;
+    p.heads = heads;
+    p.tokens_q = tokens_q;
+    p.tokens_kv = tokens_kv;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.out_bf16 = out_dtype == NB200_BF16;
+    const size_t smem = sizeof(SmemA) + 1024;
+    if (int rc2 = set_max_smem_once(reinterpret_cast<const void *>(attention_fp16_kernel), smem)) return rc2;
+    LaunchCfg lc(dim3(tokens_q / kBM, heads, batch), dim3(kThreadsAttn), smem, stream);
+    NB200_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, attention_fp16_kernel, tm_q, tm_k, tm_v, p));
+    count_launch();
+    return NB200_OK;
+}

@@ -34,6 +34,8 @@
 #include "ptx.cuh"
 
 namespace nb200 {
+
+int rope_inplace_dispatch(int dtype, void *qkv, int M, int N, const void *norm_q, const void *norm_k, const float *rotary, cudaStream_t stream);
 namespace {
 
 using namespace ptx;
@@ -69,6 +71,8 @@ struct ClusterParams {
     __half *out_qkv[3];
     long long stride_head[3];
     int attn_tokens;
+    void *out;                   // hT [M_out, N_out] row-major (null with PackQKV)
+    int M_out, N_out;
     long long *prof;
     int debug;
     float lora_scales[NB200_MAX_LORA_SCALES];
@@ -180,7 +184,6 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
         prefetch_tensormap(&tm_sfa);
         prefetch_tensormap(&tm_sfb);
         if (p.has_lora) prefetch_tensormap(&tm_lu);
-        if (p.out_qkv[0] == nullptr) prefetch_tensormap(&tm_out);
     }
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < kStages; i++) {
@@ -577,8 +580,10 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
             // one 64-column chunk (cc = 0, 1 inside this group's half): scale / bias / activation / RoPE, hT pack, store
             auto do_chunk = [&](const int cc, const uint32_t(&v0)[32], const uint32_t(&v1)[32]) {
                 const int ch = h * 2 + cc;   // chunk inside the 256-wide tile
-                if (et == 0 && !pack_qkv) bulk_wait_group_read<0>();
-                if (!pack_qkv) named_bar_sync(2 + 2 * h, 128);
+                // Output tile: each warp transposes its own 32 rows x 64 columns through its 4 KB of staging (row per lane in, 4 rows x 128
+                // contiguous bytes per store instruction out).  No TMA store: it queues behind the operand loads in the SM's one TMA unit
+                // (r02 epilogue timeline: 1.4k clk until a 16 KB store had left shared memory) and needs group-wide barriers on both sides.
+                __syncwarp();   // this warp's read-out of the previous chunk is done
                 emark(5);
                 uint8_t *srow = s.out_stage[h] + row * 128;
                 [[maybe_unused]] __half *qkv_row = nullptr;
@@ -649,18 +654,23 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                 }
                 if (pack_qkv) return;
                 emark(6);
-                fence_proxy_async_smem();
-                named_bar_sync(3 + 2 * h, 128);
-                emark(7);
-                if (et == 0) {
-                    tma_store_2d(&tm_out, s.out_stage[h], n0 + ch * 64, m0);
-                    bulk_commit_group();
+                __syncwarp();
+                {
+                    const int c = lane & 7;
+                    const int col = n0 + ch * 64 + c * 8;
+                    hT *gout = static_cast<hT *>(p.out);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int r = qd * 32 + j * 4 + (lane >> 3);
+                        const uint4 v = *reinterpret_cast<const uint4 *>(s.out_stage[h] + r * 128 + ((c ^ (r & 7)) * 16));
+                        if (m0 + r < p.M_out && col < p.N_out) *reinterpret_cast<uint4 *>(gout + static_cast<size_t>(m0 + r) * p.N_out + col) = v;
+                    }
                 }
+                emark(7);
             };
             do_chunk(0, va, vb);
             do_chunk(1, vc, vd);
         }
-        if (et == 0) bulk_wait_group<0>();
         if (p.prof && eta == 0) {
             p.prof[blockIdx.x * 16 + 4] = t_tmem_full;
             p.prof[blockIdx.x * 16 + 5] = clock64() - t_epi0;
@@ -738,6 +748,9 @@ int launch_cluster(const nb200_gemm_args &a, cudaStream_t stream) {
     p.stride_head[1] = a.stride_head_k;
     p.stride_head[2] = a.stride_head_v;
     p.attn_tokens = a.attn_tokens;
+    p.out = a.out;
+    p.M_out = a.M_out;
+    p.N_out = a.N_out;
     p.prof = static_cast<long long *>(a.prof);
     const char *dbg_env = getenv("NB200_GEMM_DEBUG");   // read per launch: tools/gemm_ablate.py sweeps it inside one process
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
@@ -779,7 +792,21 @@ int launch_cluster(const nb200_gemm_args &a, cudaStream_t stream) {
 
 template <typename hT>
 int dispatch_t(const nb200_gemm_args &a, cudaStream_t stream, int pairs) {
-    const bool rope = a.rotary_emb != nullptr;
+    bool rope = a.rotary_emb != nullptr;
+    // QKV with a plain [M, N] output: the GEMM with its default epilogue followed by the in-place RMSNorm + RoPE kernel (rope.cu) beats
+    // the fused epilogue by a wide margin on these tile shapes (115.6 -> ~80 us at 4352 x 3072 -> 9216: the rotary table is 128 KB of
+    // extra ingest per tile when every epilogue thread fetches its own row).  Bit-identical results; NB200_ROPE_SPLIT=0 keeps it fused.
+    // PackQKV (three fp16 outputs) stays fused: it has no [M, N] buffer to work in.
+    const char *split_env = getenv("NB200_ROPE_SPLIT");   // read per launch (tests and tools flip it inside one process)
+    const bool split_enabled = !(split_env && atoi(split_env) == 0);
+    if (rope && a.out != nullptr && a.out_q == nullptr && a.N_out == a.N && split_enabled) {
+        nb200_gemm_args plain = a;
+        plain.rotary_emb = nullptr;
+        plain.norm_q = plain.norm_k = nullptr;
+        const int rc = pairs == 2 ? launch_cluster<2, hT, EPI_DEFAULT>(plain, stream) : launch_cluster<1, hT, EPI_DEFAULT>(plain, stream);
+        if (rc != NB200_OK) return rc;
+        return rope_inplace_dispatch(a.dtype, a.out, a.M_out, a.N, a.norm_q, a.norm_k, a.rotary_emb, stream);
+    }
     if (pairs == 2) return rope ? launch_cluster<2, hT, EPI_ROPE>(a, stream) : launch_cluster<2, hT, EPI_DEFAULT>(a, stream);
     return rope ? launch_cluster<1, hT, EPI_ROPE>(a, stream) : launch_cluster<1, hT, EPI_DEFAULT>(a, stream);
 }

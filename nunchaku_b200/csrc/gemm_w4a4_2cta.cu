@@ -402,7 +402,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                     *reinterpret_cast<uint4 *>(dst + o * 128) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
                 fence_proxy_async_smem();
-                mbar_arrive_cluster(lora_a_full_leader);
+                mbar_arrive_remote(lora_a_full_leader);
                 lora_phase ^= 1;
             }
 
@@ -473,7 +473,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                 tmem_ld_32x32b_x32(taddr + ch0 * 64 + 96, vd);
                 tmem_ld_wait();
                 tc_fence_before_sync();
-                mbar_arrive_cluster(tmem_empty_leader);
+                mbar_arrive_remote(tmem_empty_leader);
                 if (!(p.debug & 8)) {
                     do_chunk(ch0, va, vb);
                     do_chunk(ch0 + 1, vc, vd);
@@ -488,7 +488,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                     tmem_ld_wait();
                     if (cc == CH / H - 1) {
                         tc_fence_before_sync();
-                        mbar_arrive_cluster(tmem_empty_leader);
+                        mbar_arrive_remote(tmem_empty_leader);
                     }
                     if (!(p.debug & 8)) do_chunk(ch, v0, v1);
                 }
@@ -528,7 +528,7 @@ gemm_w4a4_2cta_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_c
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {  // one arrival per warp: 512 per-thread (remote) arrivals per k-block serialise on one word
-                        mbar_arrive_cluster(mapa(smem_u32(&s.cfull[cst.idx]), 0));
+                        mbar_arrive_remote(mapa(smem_u32(&s.cfull[cst.idx]), 0));
                         mbar_arrive(&s.empty[pst.idx]);
                     }
                     t_conv += clock64() - t_c0;

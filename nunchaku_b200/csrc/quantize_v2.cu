@@ -18,6 +18,8 @@
 //     the LAST CTA of a row block (atomic ticket) sums them in split order -> still deterministic.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -260,17 +262,38 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                 if (chunk == 0 && !(p.debug & 2)) {
                     const int m = row0 + lane;
                     const uint32_t row_addr = tile + lane * 128;
-                    // phase 1: smoothing division (rounded to hT, written back over the lane's own row of the tile) + absmax
+                    // smoothing division of 8 values (4 hT pairs) by the hoisted reciprocals, rounded to hT like h2div; kSlow = a denormal factor
+                    // somewhere in the group (warp-uniform): only then the 2^24 pre-scale of __fdividef's slow branch is applied
+                    auto smooth8 = [&](uint32_t (&xw)[4], const int j, auto slow_tag) {
+                        constexpr bool kSlow = decltype(slow_tag)::value;
+                        const float4 r0 = *reinterpret_cast<const float4 *>(&s.rsm[warp][j * 8]);
+                        const float4 r1 = *reinterpret_cast<const float4 *>(&s.rsm[warp][j * 8 + 4]);
+                        const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            float2 a = Tr::to_float2(*reinterpret_cast<const T2 *>(&xw[e]));
+                            if constexpr (kSlow) {
+                                a.x = (a.x * s.ksm[warp][j * 8 + 2 * e]) * rr[2 * e];
+                                a.y = (a.y * s.ksm[warp][j * 8 + 2 * e + 1]) * rr[2 * e + 1];
+                            } else {          // pre-scale == 1: (a * 1) * r == a * r bit for bit
+                                a.x = a.x * rr[2 * e];
+                                a.y = a.y * rr[2 * e + 1];
+                            }
+                            const T2 h = Tr::from_float2(a);   // h2div rounds the quotient to hT
+                            xw[e] = *reinterpret_cast<const uint32_t *>(&h);
+                        }
+                    };
+                    // INT4, phase 1: smoothing division (written back over the lane's own row of the tile) + absmax of the whole 64-group
                     T2 amax2;          // running |x| max of both halves, NaN-propagating
                     amax2.x = Tr::from_float(0.f);
                     amax2.y = amax2.x;
                     [[maybe_unused]] T2 vmin2 = amax2;   // unsigned mode: a negative value needs the saturating slow path
+                    auto int4_phase1 = [&](auto slow_tag) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const uint32_t addr = row_addr + ((j ^ (lane & 7)) << 4);
-                        const uint4 xv = lds_v4(addr);
-                        uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                        if constexpr (!FP4) {
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t addr = row_addr + ((j ^ (lane & 7)) << 4);
+                            const uint4 xv = lds_v4(addr);
+                            uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
                             if (p.unsigned_shift) {   // the fused GELU epilogue's shift, added in hT (launch_impl:286, half2 add)
                                 T2 sh2;
                                 sh2.x = Tr::from_float(0.171875f);
@@ -281,35 +304,20 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                                     xw[e] = *reinterpret_cast<const uint32_t *>(&v);
                                 }
                             }
-                        }
-                        if (smooth != nullptr) {
-                            const float4 r0 = *reinterpret_cast<const float4 *>(&s.rsm[warp][j * 8]);
-                            const float4 r1 = *reinterpret_cast<const float4 *>(&s.rsm[warp][j * 8 + 4]);
-                            const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                            if (smooth != nullptr) smooth8(xw, j, slow_tag);
+                            if (smooth != nullptr || p.unsigned_shift) sts_v4(addr, xw);
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
-                                float2 a = Tr::to_float2(*reinterpret_cast<const T2 *>(&xw[e]));
-                                if (slow_div) {   // x / smooth as __fdividef computes it, denormal divisor branch
-                                    a.x = (a.x * s.ksm[warp][j * 8 + 2 * e]) * rr[2 * e];
-                                    a.y = (a.y * s.ksm[warp][j * 8 + 2 * e + 1]) * rr[2 * e + 1];
-                                } else {          // ksm == 1: (a * 1) * r == a * r bit for bit
-                                    a.x = a.x * rr[2 * e];
-                                    a.y = a.y * rr[2 * e + 1];
-                                }
-                                const T2 h = Tr::from_float2(a);   // h2div rounds the quotient to hT
-                                xw[e] = *reinterpret_cast<const uint32_t *>(&h);
-                            }
-                        }
-                        if (smooth != nullptr || (!FP4 && p.unsigned_shift)) sts_v4(addr, xw);
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            amax2 = __hmax2_nan(amax2, __habs2(*reinterpret_cast<const T2 *>(&xw[e])));
-                            if constexpr (!FP4) {
+                                amax2 = __hmax2_nan(amax2, __habs2(*reinterpret_cast<const T2 *>(&xw[e])));
                                 if (p.unsigned_shift) vmin2 = __hmin2(vmin2, *reinterpret_cast<const T2 *>(&xw[e]));
                             }
                         }
+                    };
+                    if constexpr (!FP4) {
+                        if (slow_div) int4_phase1(std::true_type{});
+                        else int4_phase1(std::false_type{});
                     }
-                    // phase 2 re-reads the (rounded) row: the 64 values never sit in registers together
+                    // (INT4: phase 2 re-reads the rounded row: the 64 values never sit in registers together)
                     auto load_chunk = [&](int j, uint32_t (&xw)[4]) {
                         const uint4 xv = lds_v4(row_addr + ((j ^ (lane & 7)) << 4));
                         xw[0] = xv.x;
@@ -389,41 +397,46 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                             *reinterpret_cast<uint32_t *>(qdst) = words[1] ^ words[2] ^ words[4] ^ words[5] ^ words[6] ^ words[7];
                         }
                     } else {
+                        // NVFP4: ONE pass -- a 16-element micro-group (2 chunks) is smoothed, rounded to hT, scaled and converted in registers;
+                        // nothing is written back to the tile (r02: the two-pass version spent 16 of its LDS / STS.128 and a proxy fence per
+                        // group on the round trip)
                         uint32_t words[8];
                         uint32_t sfw = 0;
+                        auto fp4_pass = [&](auto slow_tag) {
 #pragma unroll
-                        for (int g16 = 0; g16 < 4; g16++) {   // 16-element micro-groups: chunks 2*g16, 2*g16+1
-                            uint32_t xg[8];
-                            {
-                                uint32_t t0[4], t1[4];
-                                load_chunk(2 * g16, t0);
-                                load_chunk(2 * g16 + 1, t1);
+                            for (int g16 = 0; g16 < 4; g16++) {   // 16-element micro-groups: chunks 2*g16, 2*g16+1
+                                uint32_t xg[8];
 #pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    xg[i] = t0[i];
-                                    xg[4 + i] = t1[i];
+                                for (int c = 0; c < 2; c++) {
+                                    uint32_t xw[4];
+                                    load_chunk(2 * g16 + c, xw);
+                                    if (smooth != nullptr) smooth8(xw, 2 * g16 + c, slow_tag);
+#pragma unroll
+                                    for (int i = 0; i < 4; i++) xg[4 * c + i] = xw[i];
+                                }
+                                float amax = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 8; i++) {
+                                    const float2 f = Tr::to_float2(*reinterpret_cast<const T2 *>(&xg[i]));
+                                    amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+                                }
+                                const float sc = fminf(amax * (1.0f / 6.0f), 448.0f);
+                                const float rs = rcp_approx_ftz(sc);
+                                sfw |= (cvt_e4m3x2(0.f, sc) & 0xFFu) << (8 * g16);
+#pragma unroll
+                                for (int w2 = 0; w2 < 2; w2++) {
+                                    uint32_t wv = 0;
+#pragma unroll
+                                    for (int e = 0; e < 4; e++) {
+                                        const float2 f = Tr::to_float2(*reinterpret_cast<const T2 *>(&xg[w2 * 4 + e]));
+                                        wv |= cvt_e2m1x2(f.y * rs, f.x * rs) << (8 * e);
+                                    }
+                                    words[g16 * 2 + w2] = wv;
                                 }
                             }
-                            float amax = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                const float2 f = Tr::to_float2(*reinterpret_cast<const T2 *>(&xg[i]));
-                                amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
-                            }
-                            const float sc = fminf(amax * (1.0f / 6.0f), 448.0f);
-                            const float rs = rcp_approx_ftz(sc);
-                            sfw |= (cvt_e4m3x2(0.f, sc) & 0xFFu) << (8 * g16);
-#pragma unroll
-                            for (int w2 = 0; w2 < 2; w2++) {
-                                uint32_t wv = 0;
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    const float2 f = Tr::to_float2(*reinterpret_cast<const T2 *>(&xg[w2 * 4 + e]));
-                                    wv |= cvt_e2m1x2(f.y * rs, f.x * rs) << (8 * e);
-                                }
-                                words[g16 * 2 + w2] = wv;
-                            }
-                        }
+                        };
+                        if (slow_div) fp4_pass(std::true_type{});
+                        else fp4_pass(std::false_type{});
                         uint8_t *sf = reinterpret_cast<uint8_t *>(p.scales) + (static_cast<size_t>(m >> 7) * G + g) * 512 + (m & 31) * 16 +
                                       ((m & 127) >> 5) * 4;
                         if (!(p.debug & 4)) {
@@ -435,7 +448,7 @@ quantize_v2_kernel(const __grid_constant__ CUtensorMap tm_x, const Q2Params p) {
                         }
                     }
                 }
-                if (chunk == 0 && (smooth != nullptr || (!FP4 && p.unsigned_shift))) fence_proxy_async_smem();   // our in-place writes vs the TMA refill of this stage
+                if (!FP4 && chunk == 0 && (smooth != nullptr || p.unsigned_shift)) fence_proxy_async_smem();   // INT4's in-place writes vs the TMA refill of this stage
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.empty[st]);
             }

@@ -88,6 +88,40 @@ class SVDQW4A4Linear(nn.Module):
         """Call after changing parameters in place (LoRA merge, ``param.data.copy_``); ``load_state_dict`` does it itself."""
         self._b200 = None
 
+    def _source_fingerprint(self) -> str:
+        return B200Weights.fingerprint(qweight=self.qweight.data, wscales=self.wscales.data, bias=None if self.bias is None else self.bias.data,
+                                       smooth=self.smooth_factor.data, proj_down=self.proj_down.data, proj_up=self.proj_up.data,
+                                       wcscales=None if self.wcscales is None else self.wcscales.data, alpha=self.wtscale, precision=self.precision)
+
+    def save_b200(self, path: str) -> None:
+        """Write the converted layer to a side-car file: ``load_b200`` on a later start skips the conversion, and -- with
+        ``require_source=False`` on a module whose checkpoint-layout tensors were never loaded -- the checkpoint-layout copy as well."""
+        if self.qweight.numel() == 0:
+            raise RuntimeError("the checkpoint-layout parameters were released: save the side-car before release_reference_layout()")
+        state = self.b200().state()
+        state["source_sha256"] = self._source_fingerprint()
+        state["precision"], state["act_unsigned"] = self.precision, bool(self.act_unsigned)
+        torch.save(state, path)
+
+    def load_b200(self, path: str, *, require_source: bool = True) -> None:
+        """Adopt a side-car written by ``save_b200``.  ``require_source=True`` (default): the file must have been made from exactly the
+        parameters this module holds now (sha256 of their bytes), otherwise ValueError.  ``require_source=False``: trust the file (geometry
+        and precision are still checked) -- for deployments that ship only the side-car; the module's checkpoint-layout tensors are then
+        released."""
+        state = torch.load(path, map_location="cpu", weights_only=True)
+        if state.get("precision") != self.precision or int(state["N"]) != self.out_features or int(state["K"]) != self.in_features or \
+                int(state["rank"]) != self.rank:
+            raise ValueError("B200 side-car does not match this layer's geometry / precision")
+        if require_source:
+            if self.qweight.numel() == 0 or state.get("source_sha256") != self._source_fingerprint():
+                raise ValueError("B200 side-car was made from different parameters than this module holds")
+        self._b200 = B200Weights.from_state(state, self.qweight.device)
+        self._b200_alpha = self.wtscale
+        if not require_source:
+            for name in ("qweight", "wscales"):
+                p = getattr(self, name)
+                p.data = torch.empty(0, dtype=p.dtype, device=p.device)
+
     def release_reference_layout(self) -> int:
         """Convert, then free the checkpoint-layout storage of the big tensors (halves the resident weight memory; the
         reference keeps only its own layout).  The state dict of a released module is no longer loadable elsewhere.

@@ -8,7 +8,8 @@ resident weight memory.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+import hashlib
+from dataclasses import dataclass, fields
 
 import torch
 
@@ -56,6 +57,50 @@ class B200Weights:
             lora_down_next=repack.lora_down_next(proj_down, cache=False) if rank > 0 else None,
             smooth=None if smooth is None else repack.channel_vector(smooth, out_f32=False, cache=False),
         )
+
+    # ---- side-car persistence ------------------------------------------------------------------
+    # The conversion is a pure function of the checkpoint tensors, so a deployment can do it once, keep the result next to the
+    # checkpoint and skip both the repack kernels and the checkpoint-layout copy on every later start.  The file is a plain
+    # ``torch.save`` dict of CPU tensors + geometry + a fingerprint of the source tensors it was made from.
+    FORMAT = 1
+
+    def state(self) -> dict:
+        out = {"format": self.FORMAT, "N": self.N, "K": self.K, "rank": self.rank, "fp4": self.fp4, "dtype": str(self.dtype).replace("torch.", "")}
+        for f in fields(self):
+            v = getattr(self, f.name)
+            if isinstance(v, torch.Tensor):
+                out["t." + f.name] = v.detach().cpu()
+        return out
+
+    @classmethod
+    def from_state(cls, state: dict, device) -> "B200Weights":
+        if state.get("format") != cls.FORMAT:
+            raise ValueError(f"unsupported B200Weights side-car format {state.get('format')!r} (this build reads {cls.FORMAT})")
+        kw = {"N": int(state["N"]), "K": int(state["K"]), "rank": int(state["rank"]), "fp4": bool(state["fp4"]), "dtype": getattr(torch, state["dtype"])}
+        for f in fields(cls):
+            if f.name in kw:
+                continue
+            t = state.get("t." + f.name)
+            kw[f.name] = None if t is None else t.to(device)
+        w = cls(**kw)
+        if w.qweight is None or tuple(w.qweight.shape) != (w.N, w.K // 2):
+            raise ValueError("corrupt B200Weights side-car: qweight shape does not match its geometry")
+        return w
+
+    @staticmethod
+    def fingerprint(**tensors) -> str:
+        """sha256 over the raw bytes of the checkpoint tensors (and alpha) a bundle was converted from: a side-car is only reused for
+        the checkpoint it was made from."""
+        h = hashlib.sha256()
+        for name in sorted(tensors):
+            v = tensors[name]
+            h.update(name.encode())
+            if isinstance(v, torch.Tensor):
+                h.update(str(tuple(v.shape)).encode() + str(v.dtype).encode())
+                h.update(v.detach().contiguous().cpu().view(torch.uint8).numpy().tobytes())
+            else:
+                h.update(repr(v).encode())
+        return h.hexdigest()
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in (self.qweight, self.wscales, self.bias, self.cscale, self.lora_up, self.lora_down,

@@ -10,6 +10,8 @@ Tolerances:
     <= 2e-3, |step| <= 1;
   * lora_act_out vs fp64 matmul of the stored tile: rel-Frobenius <= 1e-4 (fp32 atomics order).
 """
+import os
+
 import pytest
 import torch
 
@@ -360,11 +362,18 @@ def test_qkv_rmsnorm_rope_cluster_kernel(hT, block_n, H):
     outs = [torch.full((1, H, Mp, 128), 7.0, dtype=torch.float16, device="cuda") for _ in range(3)]
     G.BLOCK_N_OVERRIDE = block_n
     try:
-        svdq_gemm_w4a4_cuda(out=out, **common)
+        svdq_gemm_w4a4_cuda(out=out, **common)          # default route: plain GEMM + in-place RMSNorm/RoPE kernel (csrc/rope.cu)
+        out_fused = torch.full((Mp, N), float("nan"), dtype=hT, device="cuda")
+        os.environ["NB200_ROPE_SPLIT"] = "0"            # the same call with the epilogue fused
+        try:
+            svdq_gemm_w4a4_cuda(out=out_fused, **common)
+        finally:
+            del os.environ["NB200_ROPE_SPLIT"]
         svdq_gemm_w4a4_cuda(out_q=outs[0], out_k=outs[1], out_v=outs[2], attn_tokens=M, **common)
         torch.cuda.synchronize()
     finally:
         G.BLOCK_N_OVERRIDE = 0
+    assert torch.equal(out.view(torch.int16), out_fused.view(torch.int16)), "split and fused RoPE routes must agree bit for bit"
     kw = dict(qa=qa.q, ascales=qa.scales, qw=layer.qw, wscales=layer.wscales, hT=hT, M=M, bias=layer.bias, lora_act=qa.lora_act,
               lora_up=layer.lora_up, fp4=True, alpha=layer.alpha, wcscales=layer.wcscales, rope=(norm_q, norm_k, rsin, rcos))
     _assert_parity(out[:M], O.gemm_w4a4(mode="exact", **kw).out, O.gemm_w4a4(mode="ref", **kw).out, hT, f"cluster rope bn={block_n} H={H} {hT}")

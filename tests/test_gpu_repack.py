@@ -203,3 +203,37 @@ def test_layer_on_second_gpu_while_first_is_current():
         y1 = m1(x.to("cuda:1").view(1, 300, 256))
         torch.cuda.synchronize("cuda:1")
         assert torch.equal(y0.cpu(), y1.cpu())
+
+
+@pytest.mark.parametrize("fp4", [False, True])
+def test_sidecar_of_converted_weights(tmp_path, fp4):
+    """SURVEY N4: save_b200 -> a fresh module adopts the file (no repack kernels, checkpoint-layout copy optional) -> bit-identical outputs;
+    a side-car made from other parameters is refused"""
+    from oracle import svdq as O
+
+    hT = torch.bfloat16
+    layer = O.make_synthetic_layer(256, 256, 32, fp4=fp4, hT=hT, seed=331)
+    other = O.make_synthetic_layer(256, 256, 32, fp4=fp4, hT=hT, seed=332)
+    prec = "nvfp4" if fp4 else "int4"
+    m, sd = _module(layer, prec)
+    x = O.make_activations(200, 256, hT, seed=333, smooth=layer.smooth).cuda().view(1, 200, 256)
+    y = m(x)
+    path = str(tmp_path / "l.b200")
+    m.save_b200(path)
+    # (a) same checkpoint loaded again: the side-car replaces the conversion
+    m2, _ = _module(layer, prec)
+    m2.load_b200(path)
+    assert torch.equal(m2(x), y)
+    # (b) side-car only: the module never sees the checkpoint-layout weight tensors
+    from nunchaku_b200.models.linear import SVDQW4A4Linear
+
+    m3 = SVDQW4A4Linear(256, 256, rank=32, bias=True, precision=prec, torch_dtype=hT, device="cuda")
+    if fp4:
+        m3.wtscale = layer.alpha
+    m3.load_b200(path, require_source=False)
+    assert m3.qweight.numel() == 0 and torch.equal(m3(x), y)
+    # (c) a module holding OTHER parameters refuses it
+    m4, _ = _module(other, prec)
+    with pytest.raises(ValueError, match="different parameters"):
+        m4.load_b200(path)
+    torch.cuda.synchronize()

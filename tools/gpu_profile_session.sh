@@ -1,27 +1,23 @@
 #!/bin/bash
-# Profiling session: ALU micro-benchmark, ncu launch lists of one bench step, ncu --set full of the top kernels,
-# then the two bench lines (never under ncu).
+# Profiling session (one GPU): ncu launch list of one bench step (eager launches, same workload as the default command), ncu --set full of the
+# top GEMM and of the quantizer, then the bench line itself (never under ncu).
+#   bash tools/gpu_profile_session.sh <tag>
 set -x
 mkdir -p gpurun_out
-TAG=${1:-r01i}
-LAUNCHES=${2:-589}   # kernels per bench step: 304 GEMM + 228 quantize + 57 more quantizes of the split large-M MLPs
-nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/ubench/alu_rates.cu -o gpurun_out/alu_rates && ./gpurun_out/alu_rates | tee gpurun_out/alu_rates_${TAG}.txt
-rm -f gpurun_out/alu_rates
-K='regex:gemm_w4a4|quantize'
-for P in int4 nvfp4; do
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s $((3 * LAUNCHES)) -c $LAUNCHES --csv --log-file gpurun_out/launches_${TAG}_$P.csv \
-      python bench.py --steps 1 --warmup 3 --precision $P --no-graph --skip-cpu > gpurun_out/ncu_b_$P.log 2>&1
-  tail -2 gpurun_out/ncu_b_$P.log
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_w4a4 -s 3 -c 1 -o gpurun_out/prof_${TAG}_gemm_${P} -f \
-      python tools/op_sweep.py --precision $P --shapes primary --iters 3 --bn 0 --out gpurun_out/tmp.json > gpurun_out/ncu_full_${P}.log 2>&1
-  tail -2 gpurun_out/ncu_full_${P}.log
-done
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:quantize_v2 -s 3 -c 1 -o gpurun_out/prof_${TAG}_quant_int4 -f \
-    python tools/op_sweep.py --precision int4 --shapes primary --iters 3 --bn 0 --out gpurun_out/tmp.json > gpurun_out/ncu_fullq.log 2>&1
-tail -2 gpurun_out/ncu_fullq.log
-for P in int4 nvfp4; do
-  python bench.py --steps 8 --warmup 3 --precision $P > gpurun_out/bench_${TAG}_$P.json 2> gpurun_out/bench_${TAG}_$P.err
-  cat gpurun_out/bench_${TAG}_$P.json | cut -c1-600
-  tail -3 gpurun_out/bench_${TAG}_$P.err
-done
-ls -la gpurun_out | tail -20
+TAG=${1:-r02e}
+# our kernels only (torch's weight-initialisation kernels come first and are not part of a step); an eager step launches ~570 of them:
+# skip the 3 warm-up steps, list one timed step
+K='regex:gemm_|quantize_|norm_|add_kernel|mul_add_kernel|activation_kernel|cast_kernel|split_mod|gemv_awq|litela'
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -s 1710 -c 570 --csv --log-file gpurun_out/launches_${TAG}_nvfp4.csv \
+    python bench.py --steps 1 --warmup 3 --no-graph --skip-cpu --no-secondary --no-legs > gpurun_out/ncu_b_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_b_${TAG}.log | cut -c1-300
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_nvfp4_cluster -c 2 -o gpurun_out/prof_${TAG}_gemm_nvfp4 -f \
+    python tools/ncu_gemm_one.py --precision nvfp4 --bn 1024 > gpurun_out/ncu_full_gemm_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_full_gemm_${TAG}.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:quantize_v2 -c 2 -o gpurun_out/prof_${TAG}_quant_nvfp4 -f \
+    python tools/ncu_quant_one.py --precision nvfp4 > gpurun_out/ncu_full_quant_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_full_quant_${TAG}.log
+python bench.py > gpurun_out/bench_${TAG}_nvfp4.json 2> gpurun_out/bench_${TAG}_nvfp4.err
+tail -c 1500 gpurun_out/bench_${TAG}_nvfp4.json
+tail -3 gpurun_out/bench_${TAG}_nvfp4.err
+ls -la gpurun_out | tail -12
