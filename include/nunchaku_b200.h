@@ -231,6 +231,16 @@ int nb200_linearattn_vk_mul_q(int dtype, void *q, const float *vk, int batch, in
 int nb200_gemv_awq(int dtype, const void *x, const void *qweight, const void *scales, const void *zeros, void *out, int M, int OC, int IC,
                    int group_size, void *stream);
 
+/* ---- scaled-dot-product attention of the FLUX blocks ------------------------------------------------
+ * o[b, i, h*128 + :] = softmax_j(scale * q[b,h,i,:] . k[b,h,j,:]) @ v[b,h,j,:], non-causal, head_dim 128.
+ * Replaces nunchaku::kernels::attention_fp16 (src/kernels/zgemm/attention.cu:10-94, zgemm.h:70-74; nunchaku/csrc/ops.h attention_fp16).
+ * q / k / v: fp16 [batch, heads, tokens, 128] contiguous, ROW-MAJOR inside a head -- what nb200_gemm_w4a4's PackQKV epilogue writes (the
+ * reference keeps its mma.sync fragment order there).  Pad rows of K hold NaN and act as the key mask (NaN score -> -inf), pad rows of Q
+ * are 0, of V 0, exactly as that epilogue produces them.  o: fp16 / bf16 (out_dtype) [batch, tokens_q, heads * 128].
+ * tokens_q and tokens_kv must be multiples of 128 (the reference: 128 / 32).  Both GEMMs run on tcgen05 with fp32 accumulation. */
+int nb200_attention_fp16(const void *q, const void *k, const void *v, void *o, int out_dtype, int batch, int heads, int tokens_q, int tokens_kv,
+                         float scale, void *stream);
+
 /* Number of kernels the last nb200_* call on this thread launched (bench bookkeeping). */
 int nb200_last_launch_count(void);
 

@@ -110,6 +110,7 @@ SYMBOLS = {
     "nb200_cast": (c_int, [c_int, c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
     "nb200_litela_vk": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "nb200_linearattn_vk_mul_q": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "nb200_attention_fp16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "nb200_gemv_awq": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -11,7 +11,8 @@
 // (zgemm_b200.cpp -> libnunchaku_b200.so).  Built by oracle/ref_build/build_ref.sh into oracle/_ref/pyseam/_C.so;
 // tests/test_gpu_seam_pybind.py imports it and checks it against the Python operator layer bit for bit.
 //
-// Out-of-scope entries of ops.h (attention_fp16, gemm_awq, test_*) are registered too, because ops.h defines them, and raise.
+// `_C.ops.attention_fp16` and `_C.ops.gemv_awq` resolve to our kernels as well (zgemm_b200.cpp, awq_b200.cpp).  The remaining entries of
+// ops.h (gemm_awq, test_*) are registered too, because ops.h defines them, and raise.
 #include <torch/extension.h>
 
 #include "ops.h"   // the reference's nunchaku/csrc/ops.h
@@ -20,8 +21,7 @@ namespace nunchaku::kernels {
 void b200_invalidate_all();
 void b200_set_identity(const void *device_ptr, uint64_t token);
 void b200_clear_identities();
-// out-of-scope kernels that ops.h references: not provided by the B200 library (SURVEY section 8f rows N1 / N2 are "next")
-void attention_fp16(Tensor, Tensor, Tensor, Tensor, float) { throw std::runtime_error("attention_fp16: not provided by nunchaku_b200 (SURVEY N1)"); }
+// reference-internal test hooks that ops.h references: not provided by the B200 library
 void test_rmsnorm_rope(Tensor, Tensor, Tensor, Tensor, Tensor) { throw std::runtime_error("test_rmsnorm_rope: reference-internal test hook, not provided"); }
 void test_pack_qkv(Tensor, Tensor, Tensor, Tensor, int) { throw std::runtime_error("test_pack_qkv: reference-internal test hook, not provided"); }
 }  // namespace nunchaku::kernels

@@ -311,6 +311,18 @@ void linearattn_vk_mul_q(Tensor q, Tensor vk) {
     check(nb200_linearattn_vk_mul_q(dtype_of(q), q.data_ptr(), vk.data_ptr<float>(), batch, tokens, heads, 1e-6f, stream()), "nb200_linearattn_vk_mul_q");
 }
 
+// ---- zgemm.h:70-74 -------------------------------------------------------------------------------------------------
+// q / k / v: what OUR PackQKV epilogue wrote into out_q / out_k / out_v (same shapes and dtype as the reference's, row-major inside a head)
+void attention_fp16(Tensor q, Tensor k, Tensor v, Tensor o, float scale) {
+    if (q.scalar_type() != Tensor::FP16 || k.scalar_type() != Tensor::FP16 || v.scalar_type() != Tensor::FP16)
+        throw std::invalid_argument("attention_fp16: q / k / v must be fp16");
+    const int batch = q.shape[0], heads = q.shape[1], tokens_q = q.shape[2], tokens_kv = k.shape[2];
+    if (q.shape[3] != 128 || o.ndims() != 3 || o.shape[0] != batch || o.shape[1] != tokens_q || o.shape[2] != heads * 128)
+        throw std::invalid_argument("attention_fp16: q [B, H, Tq, 128], o [B, Tq, H * 128] expected (attention.cu:21-24)");
+    check(nb200_attention_fp16(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dtype_of(o), batch, heads, tokens_q, tokens_kv, scale, stream()),
+          "nb200_attention_fp16");
+}
+
 // not reachable from Linear.cpp / FluxModel.cpp / SanaModel.cpp; kept so every zgemm.h W4A4 symbol resolves
 void quantize_w4a4_act(Tensor, Tensor, Tensor) { throw std::runtime_error("quantize_w4a4_act: unused by the reference's models; not provided"); }
 void quantize_w4a4_wgt(Tensor, Tensor, Tensor) { throw std::runtime_error("quantize_w4a4_wgt: offline tool; not provided"); }

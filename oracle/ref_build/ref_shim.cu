@@ -152,10 +152,11 @@ int nref_linearattn_vk_mul_q(const nref_tensor *q, const nref_tensor *vk, void *
     return guarded(stream, [&] { nunchaku::kernels::linearattn_vk_mul_q(wrap(q), wrap(vk)); });
 }
 
-#ifndef NREF_SEAM_BUILD
+// (both builds: in the seam library `attention_fp16` is OUR definition and consumes OUR PackQKV layout)
 int nref_attention_fp16(const nref_tensor *q, const nref_tensor *k, const nref_tensor *v, const nref_tensor *o, float scale, void *stream) {
     return guarded(stream, [&] { nunchaku::kernels::attention_fp16(wrap(q), wrap(k), wrap(v), wrap(o), scale); });
 }
+#ifndef NREF_SEAM_BUILD
 
 int nref_test_rmsnorm_rope(const nref_tensor *input, const nref_tensor *output, const nref_tensor *norm_q, const nref_tensor *norm_k,
                            const nref_tensor *rotary_emb, void *stream) {

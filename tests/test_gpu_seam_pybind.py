@@ -95,5 +95,23 @@ def test_pybind_utils_and_out_of_scope_entries(C):
     C.utils.disable_memory_auto_release()
     C.utils.trim_memory()
     with pytest.raises(RuntimeError, match="not provided"):
-        t = torch.zeros(1, 1, 256, 128, dtype=torch.float16, device="cuda")
-        C.ops.attention_fp16(t, t, t, torch.zeros(1, 256, 128, dtype=torch.float16, device="cuda"), 1.0)
+        t = torch.zeros(1, 256, 128, dtype=torch.float16, device="cuda")
+        C.ops.test_rmsnorm_rope(t, t, torch.ones(128, dtype=torch.float16, device="cuda"), torch.ones(128, dtype=torch.float16, device="cuda"),
+                                torch.zeros(1, 256, 128, dtype=torch.float32, device="cuda"))
+
+
+def test_pybind_attention_fp16_is_our_kernel(C):
+    """`_C.ops.attention_fp16(q, k, v, o, scale)` (ops.h) on csrc/attention.cu: same result as the Python operator"""
+    from nunchaku_b200.ops.attention import attention_fp16
+    from oracle import attention as AT
+
+    g = torch.Generator().manual_seed(4)
+    qkv = (torch.randn(200, 3 * 2 * 128, generator=g) * 0.5).to(torch.float16)
+    q, k, v = (t.cuda() for t in AT.pack_qkv_rowmajor(qkv, heads=2, tokens_pad=256))
+    o1 = torch.empty(1, 256, 256, dtype=torch.float16, device="cuda")
+    o2 = torch.empty_like(o1)
+    C.ops.attention_fp16(q, k, v, o1, 128 ** -0.5)
+    attention_fp16(q, k, v, o2, 128 ** -0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(o1[:, :200], o2[:, :200])
+    assert O.rel_fro(o1[:, :200].cpu(), AT.attention_fp16(q.cpu(), k.cpu(), v.cpu(), 128 ** -0.5)[:, :200]) <= 6e-4
