@@ -56,6 +56,12 @@ def main():
     us = time_fn(lambda: attention_fp16(q, k, v, o, 128 ** -0.5), args.iters, flush)
     res["ours_us"], res["ours_tflops"] = us, flops / us / 1e6
     print(f"ours       {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
+    os.environ["NB200_ATTN_V"] = "1"   # the round's first kernel (one CTA per SM, P through shared memory), kept for this comparison
+    o1 = torch.empty_like(o)
+    us1 = time_fn(lambda: attention_fp16(q, k, v, o1, 128 ** -0.5), args.iters, flush)
+    del os.environ["NB200_ATTN_V"]
+    res["ours_v1_us"], res["v2_vs_v1_rel"] = us1, float((o[:, :T].float() - o1[:, :T].float()).norm() / o1[:, :T].float().norm())
+    print(f"ours (v1)  {us1:8.1f} us  {flops / us1 / 1e6:7.1f} TFLOP/s   v2 vs v1 rel {res['v2_vs_v1_rel']:.2e}", flush=True)
     if R.available("ref"):
         rq = torch.zeros_like(q)
         rk, rv = torch.zeros_like(q), torch.zeros_like(q)
