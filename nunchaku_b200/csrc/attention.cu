@@ -57,6 +57,7 @@ struct AttnParams {
     int heads, tokens_q, tokens_kv;
     float scale_log2;   // scale * log2(e)
     int out_bf16;
+    int debug;          // NB200_ATTN_DEBUG ablation bits (v2): 2 = always the two-pass path; results invalid: 4 = no exponentials, 8 = K / V loaded once, 16 / 32 = one eighth of the P V / Q K^T MMAs
 };
 
 // MN-major SW128 operand (V: [keys][64 d] boxes, two boxes for d = 128): start address + 16 keys per instruction;
@@ -290,6 +291,15 @@ attention_fp16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 //     inside fp16; the final division by the running sum makes the result independent of the stale maximum);
 //   * keys masked by NaN (the reference's convention, attention.cuh:192-221) are detected with one NaN-propagating max per element in
 //     the maximum pass; only tiles that contain masked keys take the path that cleans every score.
+// Measured (B200, 24 heads x 4608 tokens, tools/attn_bench.py): v1 328-340 us, v2 221-230 us (the reference kernel built for sm_100a 1066 us, the
+// library SDPA 156-170 us).  What this shape is bound by (ablations, NB200_ATTN_DEBUG): not the tensor pipe (7/8 of the MMAs removed: 231 -> 189 us)
+// and not MUFU (exponentials removed: no change) but the serial chain of one CTA -- commit -> wake-up -> tcgen05.ld round trips -> ex2 ->
+// tcgen05.st -> arrive -> P V -> Q K'^T -- of which two run per SM.  Tried on top of it and measured no faster (kept as
+// profiles/r02_attention_pingpong_experiments.patch with the timeline tool that produced the numbers): one CTA per SM with two query tiles in
+// FlashAttention-4's ping-pong order and S held in 128 registers (252 us); the same with two softmax threads per row (244 us); 64-key tiles with
+// a double-buffered S per chain (272 us: tools/ubench/mma_shapes.cu -- an N = 64 instruction costs 58 clk, N = 128 75 clk, the A-from-TMEM
+// form 79 clk against 32 / 64 / 64 nominal, so small tiles pay per instruction); every fourth pair of exponentials as a degree-3 polynomial on
+// the FMA pipes (no gain: inside one in-order warp MUFU and FMA-pipe time add up either way).
 // In-order execution of the tensor pipe is what makes the S|P alias safe: S(j+1) = Q K^T is issued after P(j) V and overwrites columns the
 // earlier instruction has finished reading.
 constexpr int kThreadsV2 = 192;    // warp 0 TMA, warp 1 TMEM alloc + MMA, warps 2-5 softmax (TMEM lane quadrant = warp & 3)
@@ -344,6 +354,7 @@ __device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
     return d;
 }
 
+
 __global__ void __launch_bounds__(kThreadsV2, 2)
 attention_fp16_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                          const AttnParams p) {
@@ -384,7 +395,7 @@ attention_fp16_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             mbar_expect_tx(&s.q_full, kTile);
             tma_load_2d(s.q, &tm_q, &s.q_full, 0, q_row0);
             tma_load_2d(s.q + kSlab, &tm_q, &s.q_full, 64, q_row0);
-            for (int j = 0; j < n_tiles; j++) {
+            for (int j = 0; j < ((p.debug & 8) ? 1 : n_tiles); j++) {   // ablation 8: one K / V tile, reused (results invalid)
                 const uint32_t ph = j & 1;
                 mbar_wait(&s.k_empty, ph ^ 1);          // S(j-1) = Q K^T has retired
                 mbar_expect_tx(&s.k_full, kTile);
@@ -405,20 +416,20 @@ attention_fp16_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
             mbar_wait(&s.q_full, 0);
             for (int j = 0; j < n_tiles; j++) {
                 const uint32_t ph = j & 1;
-                mbar_wait(&s.k_full, ph);
+                if (j == 0 || !(p.debug & 8)) mbar_wait(&s.k_full, ph);
                 tc_fence_after_sync();
 #pragma unroll
-                for (int ks = 0; ks < kD / 16; ks++) {
+                for (int ks = 0; ks < ((p.debug & 32) ? 1 : kD / 16); ks++) {   // ablation 32: one of the 8 Q K^T instructions
                     const uint32_t off = (ks >> 2) * kSlab + (ks & 3) * 32;
                     tc_mma_f16(tmem_s, make_sw128_kmajor_desc(q_addr + off), make_sw128_kmajor_desc(k_addr + off), idesc_qk, ks != 0);
                 }
                 tc_commit(&s.k_empty);
                 tc_commit(&s.s_full);
+                if (j == 0 || !(p.debug & 8)) mbar_wait(&s.v_full, ph);   // (long there: waited for first, nothing stands between P and its MMAs)
                 mbar_wait(&s.p_full, ph);     // P(j) is in TMEM and O carries the current maximum
-                mbar_wait(&s.v_full, ph);
                 tc_fence_after_sync();
 #pragma unroll
-                for (int ks = 0; ks < kBN / 16; ks++)
+                for (int ks = 0; ks < ((p.debug & 16) ? 1 : kBN / 16); ks++)   // ablation 16: one of the 8 P V instructions
                     tc_mma_f16_ts(tmem_o, tmem_p + ks * 8, make_sw128_mnmajor_desc(v_addr + ks * 16 * 128), idesc_pv, (j | ks) != 0);
                 tc_commit(&s.v_empty);
             }
@@ -435,86 +446,135 @@ attention_fp16_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         for (int j = 0; j < n_tiles; j++) {
             mbar_wait(&s.s_full, j & 1);
             tc_fence_after_sync();
-            // ---- pass 1: maximum of the row's 128 scores; a NaN (masked key) poisons mx and sends the tile down the cleaning path
-            float mx = -INFINITY;
-#pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-                uint32_t a[32], b[32];
-                tmem_ld_32x32b_x32(tmem_s + lane_base + hf * 64, a);
-                tmem_ld_32x32b_x32(tmem_s + lane_base + hf * 64 + 32, b);
-                tmem_ld_wait();
-                float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    m0 = max_nan_f32(m0, __uint_as_float(a[i]));
-                    m1 = max_nan_f32(m1, __uint_as_float(a[i + 1]));
-                    m2 = max_nan_f32(m2, __uint_as_float(b[i]));
-                    m3 = max_nan_f32(m3, __uint_as_float(b[i + 1]));
-                }
-                mx = max_nan_f32(max_nan_f32(m0, m1), max_nan_f32(m2, m3));
-            }
-            const bool masked = __any_sync(0xffffffffu, mx != mx);   // (all rows of a tile see the same masked keys)
-            if (masked) {   // NaN-dropping maximum (fmaxf returns the other operand)
-                mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < 4; c++) {
-                    uint32_t a[32];
-                    tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, a);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(a[i]));
-                }
-            }
-            const float m_tile = mx * scale;
-            float alpha = 1.f;
-            if (m_tile > m_run + kRescaleThreshold) {   // first tile: m_run = -inf, alpha = 0
-                alpha = ex2_approx_ftz(m_run - m_tile);
-                m_run = m_tile;
-            }
-            const float neg_m = m_run == -INFINITY ? 0.f : -m_run;   // (a fully masked first tile: 2^(-inf - 0) = 0, not NaN)
-            const float2 neg_m2 = make_float2(neg_m, neg_m);
-            // ---- pass 2: p = 2^(s * scale - m_run), 32 scores at a time (the next 32 are in flight meanwhile); fp16 pairs go back into
-            //      TMEM over columns S has vacated: chunk c of P = columns [16 c, 16 c + 16) <= the columns of S already consumed
-            float2 sum2 = make_float2(0.f, 0.f);
-            auto pass2 = [&](auto masked_tag) {
-                constexpr bool kMasked = decltype(masked_tag)::value;
+            // ---- fast path (every tile but the first, unless it raises the row maximum by more than 2^8 or holds masked keys): ONE pass over S
+            //      with the maximum the row already has; the fp16 probabilities wait in registers until the whole row is known to be fine
+            //      (P aliases S: nothing may be written before the decision)
+            bool slow = j == 0 || (p.debug & 2);
+            auto fast_pass = [&](auto mode_tag) {
+                constexpr int kMode = decltype(mode_tag)::value;   // 1 = default, 4 = no exponentials (ablation)
+                const float2 neg_m2 = make_float2(-m_run, -m_run);
+                float2 sum2 = make_float2(0.f, 0.f);
+                float tm0 = -INFINITY, tm1 = -INFINITY;
+                uint32_t pk[64];
                 uint32_t a[2][32];
                 tmem_ld_32x32b_x32(tmem_s + lane_base, a[0]);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     if (c < 3) tmem_ld_32x32b_x32(tmem_s + lane_base + (c + 1) * 32, a[(c + 1) & 1]);
-                    uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        float2 sv = make_float2(__uint_as_float(a[c & 1][i]), __uint_as_float(a[c & 1][i + 1]));
-                        if constexpr (kMasked) {
-                            sv.x = fmaxf(sv.x, -INFINITY);
-                            sv.y = fmaxf(sv.y, -INFINITY);
-                        }
-                        const float2 t = ffma2(sv, scale2, neg_m2);
-                        const float2 e = make_float2(ex2_approx_ftz(t.x), ex2_approx_ftz(t.y));
+                        const float2 t = ffma2(make_float2(__uint_as_float(a[c & 1][i]), __uint_as_float(a[c & 1][i + 1])), scale2, neg_m2);
+                        tm0 = max_nan_f32(tm0, t.x);
+                        tm1 = max_nan_f32(tm1, t.y);
+                        float2 e;
+                        if constexpr (kMode == 4) e = t;
+                        else e = make_float2(ex2_approx_ftz(t.x), ex2_approx_ftz(t.y));
                         sum2 = fadd2(sum2, e);
                         const __half2 h = __floats2half2_rn(e.x, e.y);
-                        pk[i >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+                        pk[c * 16 + (i >> 1)] = *reinterpret_cast<const uint32_t *>(&h);
                     }
-                    tmem_st_32x32b_x16(tmem_p + lane_base + c * 16, pk);
                     if (c < 3) tmem_ld_wait();
                 }
+                const float tmax = max_nan_f32(tm0, tm1);
+                slow = __any_sync(0xffffffffu, !(tmax <= kRescaleThreshold));   // (NaN compares false: masked keys take the slow path)
+                if (!slow) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t w[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i++) w[i] = pk[c * 16 + i];
+                        tmem_st_32x32b_x16(tmem_p + lane_base + c * 16, w);
+                    }
+                    l_run += sum2.x + sum2.y;
+                }
             };
-            if (masked) pass2(std::true_type{});
-            else pass2(std::false_type{});
-            l_run = fmaf(l_run, alpha, sum2.x + sum2.y);
-            // ---- O carries the old maximum: rescale this warp's 32 rows when one of them moved (P(j-1) V retired before S(j) was signalled)
-            if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    uint32_t ov[32];
-                    tmem_ld_32x32b_x32(tmem_o + lane_base + c * 32, ov);
+            if (!slow) {
+                if (p.debug & 4) fast_pass(std::integral_constant<int, 4>{});
+                else fast_pass(std::integral_constant<int, 1>{});
+            }
+            if (slow) {
+                // ---- pass 1: maximum of the row's 128 scores; a NaN (masked key) poisons mx and sends the tile down the cleaning path
+                float mx = -INFINITY;
+    #pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    uint32_t a[32], b[32];
+                    tmem_ld_32x32b_x32(tmem_s + lane_base + hf * 64, a);
+                    tmem_ld_32x32b_x32(tmem_s + lane_base + hf * 64 + 32, b);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i++) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-                    tmem_st_32x32b_x32(tmem_o + lane_base + c * 32, ov);
+                    float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    #pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        m0 = max_nan_f32(m0, __uint_as_float(a[i]));
+                        m1 = max_nan_f32(m1, __uint_as_float(a[i + 1]));
+                        m2 = max_nan_f32(m2, __uint_as_float(b[i]));
+                        m3 = max_nan_f32(m3, __uint_as_float(b[i + 1]));
+                    }
+                    mx = max_nan_f32(max_nan_f32(m0, m1), max_nan_f32(m2, m3));
+                }
+                const bool masked = __any_sync(0xffffffffu, mx != mx);   // (all rows of a tile see the same masked keys)
+                if (masked) {   // NaN-dropping maximum (fmaxf returns the other operand)
+                    mx = -INFINITY;
+    #pragma unroll 1
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t a[32];
+                        tmem_ld_32x32b_x32(tmem_s + lane_base + c * 32, a);
+                        tmem_ld_wait();
+    #pragma unroll
+                        for (int i = 0; i < 32; i++) mx = fmaxf(mx, __uint_as_float(a[i]));
+                    }
+                }
+                const float m_tile = mx * scale;
+                float alpha = 1.f;
+                if (m_tile > m_run + kRescaleThreshold) {   // first tile: m_run = -inf, alpha = 0
+                    alpha = ex2_approx_ftz(m_run - m_tile);
+                    m_run = m_tile;
+                }
+                const float neg_m = m_run == -INFINITY ? 0.f : -m_run;   // (a fully masked first tile: 2^(-inf - 0) = 0, not NaN)
+                const float2 neg_m2 = make_float2(neg_m, neg_m);
+                // ---- pass 2: p = 2^(s * scale - m_run), 32 scores at a time (the next 32 are in flight meanwhile); fp16 pairs go back into
+                //      TMEM over columns S has vacated: chunk c of P = columns [16 c, 16 c + 16) <= the columns of S already consumed
+                float2 sum2 = make_float2(0.f, 0.f);
+                auto pass2 = [&](auto masked_tag) {
+                    constexpr bool kMasked = decltype(masked_tag)::value;
+                    uint32_t a[2][32];
+                    tmem_ld_32x32b_x32(tmem_s + lane_base, a[0]);
+                    tmem_ld_wait();
+    #pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        if (c < 3) tmem_ld_32x32b_x32(tmem_s + lane_base + (c + 1) * 32, a[(c + 1) & 1]);
+                        uint32_t pk[16];
+    #pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float2 sv = make_float2(__uint_as_float(a[c & 1][i]), __uint_as_float(a[c & 1][i + 1]));
+                            if constexpr (kMasked) {
+                                sv.x = fmaxf(sv.x, -INFINITY);
+                                sv.y = fmaxf(sv.y, -INFINITY);
+                            }
+                            const float2 t = ffma2(sv, scale2, neg_m2);
+                            const float2 e = make_float2(ex2_approx_ftz(t.x), ex2_approx_ftz(t.y));
+                            sum2 = fadd2(sum2, e);
+                            const __half2 h = __floats2half2_rn(e.x, e.y);
+                            pk[i >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+                        }
+                        tmem_st_32x32b_x16(tmem_p + lane_base + c * 16, pk);
+                        if (c < 3) tmem_ld_wait();
+                    }
+                };
+                if (masked) pass2(std::true_type{});
+                else pass2(std::false_type{});
+                l_run = fmaf(l_run, alpha, sum2.x + sum2.y);
+                // ---- O carries the old maximum: rescale this warp's 32 rows when one of them moved (P(j-1) V retired before S(j) was signalled)
+                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+    #pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t ov[32];
+                        tmem_ld_32x32b_x32(tmem_o + lane_base + c * 32, ov);
+                        tmem_ld_wait();
+    #pragma unroll
+                        for (int i = 0; i < 32; i++) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                        tmem_st_32x32b_x32(tmem_o + lane_base + c * 32, ov);
+                    }
                 }
             }
             tmem_st_wait();
@@ -557,6 +617,7 @@ attention_fp16_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     }
 }
 
+
 }  // namespace
 }  // namespace nb200
 
@@ -590,6 +651,8 @@ extern "C" __attribute__((visibility("default"))) int nb200_attention_fp16(const
     p.tokens_kv = tokens_kv;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.out_bf16 = out_dtype == NB200_BF16;
+    const char *dbg_env = getenv("NB200_ATTN_DEBUG");
+    p.debug = dbg_env ? atoi(dbg_env) : 0;
     const char *ver_env = getenv("NB200_ATTN_V");   // 1 = the first kernel (one CTA per SM, P through shared memory); read per launch (tools/attn_bench.py)
     if (ver_env && atoi(ver_env) == 1) {
         const size_t smem = sizeof(SmemA) + 1024;

@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=4352)
     ap.add_argument("--heads", type=int, default=24)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--ablate", type=int, nargs="*", default=[], help="NB200_ATTN_DEBUG values to time as well (csrc/attention.cu)")
     args = ap.parse_args()
     from nunchaku_b200.ops.attention import attention_fp16
     from oracle import refgpu as R
@@ -56,6 +57,13 @@ def main():
     us = time_fn(lambda: attention_fp16(q, k, v, o, 128 ** -0.5), args.iters, flush)
     res["ours_us"], res["ours_tflops"] = us, flops / us / 1e6
     print(f"ours       {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
+    for bits in args.ablate:
+        os.environ["NB200_ATTN_DEBUG"] = str(bits)
+        usb = time_fn(lambda: attention_fp16(q, k, v, o, 128 ** -0.5), args.iters, flush)
+        res[f"ablate_{bits}_us"] = usb
+        print(f"  NB200_ATTN_DEBUG={bits:<3d} {usb:8.1f} us", flush=True)
+    os.environ.pop("NB200_ATTN_DEBUG", None)
+    attention_fp16(q, k, v, o, 128 ** -0.5)
     os.environ["NB200_ATTN_V"] = "1"   # the round's first kernel (one CTA per SM, P through shared memory), kept for this comparison
     o1 = torch.empty_like(o)
     us1 = time_fn(lambda: attention_fp16(q, k, v, o1, 128 ** -0.5), args.iters, flush)
