@@ -253,6 +253,94 @@ class StackRunner:
         return self.result
 
 
+class FullRunner(StackRunner):
+    """One denoising step of the WHOLE transformer (secondary figure "full_step"): what StackRunner runs plus everything SURVEY section 8(f)
+    added this round -- AdaLN modulation through the AWQ W4A16 GEMV (row N2: silu(temb) -> GEMV -> split -> LayerNorm * (1 + scale) + shift),
+    the QKV projection's PackQKV hand-off and attention_fp16 (row N1) over the joint [text; image] sequence, gates and residuals as the
+    reference's blocks apply them (src/FluxModel.cpp:JointTransformerBlock / FluxSingleTransformerBlock)."""
+
+    def __init__(self, torch, precision, dtype, device):
+        super().__init__(torch, precision, dtype, device)
+        from nunchaku_b200.ops.attention import attention_fp16
+        from nunchaku_b200.ops.gemv import AWQW4A16Linear
+
+        self.attention = attention_fp16
+        g = torch.Generator(device=device).manual_seed(4321)
+        T = IMG_TOKENS + TXT_TOKENS
+        self.Tpad = (T + 255) // 256 * 256
+        self.q = torch.zeros(1, HEADS, self.Tpad, 128, dtype=torch.float16, device=device)
+        self.k = torch.full_like(self.q, float("nan"))       # pad keys are the mask (NaN), written once
+        self.v = torch.zeros_like(self.q)
+        self.attn_out = torch.empty(1, self.Tpad, DIM, dtype=dtype, device=device)
+        self.temb = torch.randn(1, DIM, generator=g, device=device).to(dtype)
+
+        def awq(n_out):
+            m = AWQW4A16Linear(DIM, n_out, bias=True, torch_dtype=dtype, device=device)
+            with torch.no_grad():
+                m.qweight.copy_(torch.randint(-2 ** 31, 2 ** 31 - 1, m.qweight.shape, generator=g, device=device, dtype=torch.int64).to(torch.int32))
+                m.wscales.copy_((0.01 + 0.01 * torch.rand(m.wscales.shape, generator=g, device=device)).to(dtype))
+                m.wzeros.copy_((-0.08 * torch.rand(m.wzeros.shape, generator=g, device=device)).to(dtype))
+                m.bias.copy_((0.1 * torch.randn(n_out, generator=g, device=device)).to(dtype))
+            return m
+
+        # one modulation linear per stream-block: 6 * dim for the joint blocks' two streams, 3 * dim for the single blocks
+        self.mod = [awq((3 if b.tag.startswith("single") else 6) * DIM) for b in self.blocks]
+
+    def _modulate(self, i, h):
+        """AdaLayerNormZero(/Single): chunks of the modulation vector, LayerNorm(h) * (1 + scale_msa) + shift_msa"""
+        glue = self.glue
+        single = self.blocks[i].tag.startswith("single")
+        emb = self.mod[i](glue.silu(self.temb))
+        ch = glue.split_mod(emb.view(1, -1), 3 if single else 6)     # shift_msa, scale_msa, gate_msa[, shift_mlp, scale_mlp, gate_mlp]
+        n = glue.layernorm(h, None, None, 1e-6)
+        glue.mul_add_batch(n.view(1, -1, DIM), ch[1], True, 1.0, ch[0], True)
+        return n, ch
+
+    def _qkv_attn(self, blocks_rows):
+        """blocks_rows: [(block, normed input, first row in the joint sequence)] -> attention output rows [T, dim]"""
+        for b, n, row0 in blocks_rows:
+            views = tuple(t[:, :, row0:] for t in (self.q, self.k, self.v))
+            b.qkv.forward_qkv(n, b.norm_q, b.norm_k, self.rot[b.M], out_qkv=views, attn_tokens=b.M)
+        self.attention(self.q, self.k, self.v, self.attn_out, 128 ** -0.5)
+        return self.attn_out[0]
+
+    def step(self):
+        torch, glue = self.torch, self.glue
+        h_img, h_txt = self.h_img, self.h_txt
+        i = 0
+        for _ in range(N_JOINT):
+            bi, bt = self.blocks[i], self.blocks[i + 1]
+            n_img, c_img = self._modulate(i, h_img)
+            n_txt, c_txt = self._modulate(i + 1, h_txt)
+            attn = self._qkv_attn([(bt, n_txt, 0), (bi, n_img, TXT_TOKENS)])       # text tokens first, as the reference concatenates them
+            outs = []
+            for b, h, ch, rows in ((bi, h_img, c_img, slice(TXT_TOKENS, TXT_TOKENS + IMG_TOKENS)), (bt, h_txt, c_txt, slice(0, TXT_TOKENS))):
+                M = b.M
+                o = b.out.forward(attn[rows].reshape(1, M, DIM)).view(M, DIM)
+                glue.mul_add_batch(o.view(1, -1, DIM), ch[2], True, 0.0, h.view(1, -1, DIM), True)        # h + gate_msa * attn_out
+                n2 = glue.layernorm(o, None, None, 1e-6)
+                glue.mul_add_batch(n2.view(1, -1, DIM), ch[4], True, 1.0, ch[3], True)
+                f = b.fc1.forward_mlp(n2, b.fc2, fuse=self.fused._fuse_fc1(b.fc1, M))
+                glue.mul_add_batch(f.view(1, -1, DIM), ch[5], True, 0.0, o.view(1, -1, DIM), True)        # + gate_mlp * ff
+                outs.append(f)
+            h_img, h_txt = outs
+            i += 2
+        h = torch.cat([h_txt, h_img], dim=0)
+        for _ in range(N_SINGLE):
+            b = self.blocks[i]
+            M = b.M
+            n, ch = self._modulate(i, h)
+            attn = self._qkv_attn([(b, n, 0)])
+            o = b.out.forward(attn[:M].reshape(1, M, DIM)).view(M, DIM)
+            f = b.fc1.forward_mlp(n, b.fc2, fuse=self.fused._fuse_fc1(b.fc1, M))
+            s = glue.add(o, f)
+            glue.mul_add_batch(s.view(1, -1, DIM), ch[2], True, 0.0, h.view(1, -1, DIM), True)             # h + gate * (attn_out + ff)
+            h = s
+            i += 1
+        self.result.copy_(h)
+        return self.result
+
+
 class GemmRecorder:
     """Records every fused-GEMM call of one eager step (arguments kept alive) so that the GEMMs alone can be replayed from
     a CUDA graph: the roofline of the dominant kernel is measured under the same replay conditions as the step."""
@@ -293,17 +381,13 @@ class GemmRecorder:
 
 
 def capture(torch, fn):
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        fn()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=s):
-            fn()
-    torch.cuda.current_stream().wait_stream(s)
-    graph.replay()
+    """the package's own capture helper (nunchaku_b200/graph.py)"""
+    from nunchaku_b200.graph import GraphedStep
+
+    step = GraphedStep(fn, (), warmup=1)
+    step.replay()
     torch.cuda.synchronize()
-    return graph
+    return step
 
 
 def time_replays(torch, graph, n, barrier):
@@ -525,6 +609,7 @@ def main() -> int:
     ap.add_argument("--precision", default=os.environ.get("NB200_BENCH_PRECISION", "nvfp4"), choices=["int4", "nvfp4"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the other precision's device-resident measurement")
     ap.add_argument("--no-legs", action="store_true", help="skip the cuBLAS-bf16 and reference-GPU comparison legs")
+    ap.add_argument("--no-full", action="store_true", help="skip the whole-transformer-step figure (attention + AdaLN modulation on top of the linear stack)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
@@ -692,6 +777,27 @@ def main() -> int:
         if other == "int4" and "ms_per_step" in ref:
             secondary["speedup_vs_reference_gpu_kernels"] = ref["ms_per_step"] / ms2
 
+    # ---- the whole transformer step: + AdaLN modulation (AWQ GEMV), PackQKV, attention_fp16, gates -----------
+    full_step = None
+    if not args.no_full:
+        try:
+            runner3 = FullRunner(torch, args.precision, dtype, device)
+            for _ in range(args.warmup):
+                runner3.step()
+            torch.cuda.synchronize()
+            g3 = capture(torch, runner3.step)
+            ms3 = replica.max_over_ranks(time_replays(torch, g3, args.steps, barrier), device) / args.steps
+            attn_flops = 4.0 * HEADS * (IMG_TOKENS + TXT_TOKENS) ** 2 * 128 * (N_JOINT + N_SINGLE)
+            full_step = {"ms_per_step": ms3, "value": world * (1.0 / STEPS_PER_IMAGE) / (ms3 * 1e-3), "unit": "images/s", "precision": args.precision,
+                         "tflops": world * (f_main + f_lr + attn_flops) / (ms3 * 1e-3) / 1e12, "timing": "cuda graph replay",
+                         "what": "the step above plus what the linear stack leaves out: AdaLN modulation through the AWQ W4A16 GEMV (57 + 19 launches, 1.6 GB of 4-bit "
+                                 "weights), PackQKV hand-off, attention_fp16 on tcgen05 over the 4352-token joint sequence (57 launches, 13.3 TFLOP), gates and residuals; "
+                                 "text encoders / VAE / scheduler are outside the transformer and not run"}
+            del g3, runner3
+        except Exception as e:  # the headline numbers above must still be reported
+            print(f"[bench] full-step leg failed: {e!r}", file=sys.stderr)
+            full_step = {"unavailable": repr(e)}
+
     if rank == 0:
         cpu = None
         if not args.skip_cpu and world == 1:   # the CPU baseline is an N=1 figure (rank 0's host cores)
@@ -711,7 +817,7 @@ def main() -> int:
             "e2e": {"value": e2e_images, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": ("CUDA graph of the per-layer module calls" if timing_mode.startswith("cuda graph") else "module calls launched from Python per layer")
                             + " (SVDQW4A4Linear.forward / forward_qkv / forward_mlp, glue.layernorm / add); pinned host in/out every step, copies on a second stream"},
-            "gpu_launches": args.steps * launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, **legs,
+            "gpu_launches": args.steps * launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, "full_step": full_step, **legs,
         })
     replica.shutdown()
     return 0

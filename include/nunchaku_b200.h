@@ -168,7 +168,10 @@ typedef struct nb200_gemm_args {
      * src/kernels/zgemm/epilogues.cuh:427-550; wiring gemm_w4a4_launch_impl.cuh:376-393).
      * fp16 [heads, rows >= Mp, 128] each, row pitch 128, head pitch stride_head_* elements; element order is
      * plain row-major (the reference writes its own attention kernel's fragment order).  Rows >= attn_tokens are
-     * filled with 0 (Q, V) / NaN (K) exactly like the reference's mask (epilogues.cuh:479-489, 539-545).       */
+     * filled with 0 (Q, V) / NaN (K) exactly like the reference's mask (epilogues.cuh:479-489, 539-545).
+     * `out` may be given as well: then it is a SCRATCH of exactly [Mp, N] hT (M_out = Mp, N_out = N) whose contents are
+     * unspecified afterwards; the NVFP4 cluster route uses it to run the plain GEMM followed by the RMSNorm + RoPE + pack
+     * kernel instead of the fused epilogue (same bits, ~30 % faster at FLUX sizes).                              */
     void *out_q, *out_k, *out_v;
     long long stride_head_q, stride_head_k, stride_head_v;
     int attn_tokens;

@@ -36,6 +36,8 @@
 namespace nb200 {
 
 int rope_inplace_dispatch(int dtype, void *qkv, int M, int N, const void *norm_q, const void *norm_k, const float *rotary, cudaStream_t stream);
+int rope_pack_dispatch(int dtype, const void *qkv, int Mp, int N, const void *norm_q, const void *norm_k, const float *rotary, void *out_q, void *out_k,
+                       void *out_v, long long sq, long long sk, long long sv, int attn_tokens, cudaStream_t stream);
 namespace {
 
 using namespace ptx;
@@ -806,6 +808,23 @@ int dispatch_t(const nb200_gemm_args &a, cudaStream_t stream, int pairs) {
         const int rc = pairs == 2 ? launch_cluster<2, hT, EPI_DEFAULT>(plain, stream) : launch_cluster<1, hT, EPI_DEFAULT>(plain, stream);
         if (rc != NB200_OK) return rc;
         return rope_inplace_dispatch(a.dtype, a.out, a.M_out, a.N, a.norm_q, a.norm_k, a.rotary_emb, stream);
+    }
+    // PackQKV with a caller-provided [Mp, N] scratch in `out`: the same split -- plain GEMM into the scratch, then the RMSNorm + RoPE + pack kernel
+    // writes the attention operands (bit-identical to the fused epilogue, tests/test_gpu_fused.py)
+    if (rope && a.out != nullptr && a.out_q != nullptr && split_enabled) {
+        nb200_gemm_args plain = a;
+        plain.rotary_emb = nullptr;
+        plain.norm_q = plain.norm_k = nullptr;
+        plain.out_q = plain.out_k = plain.out_v = nullptr;
+        const int rc = pairs == 2 ? launch_cluster<2, hT, EPI_DEFAULT>(plain, stream) : launch_cluster<1, hT, EPI_DEFAULT>(plain, stream);
+        if (rc != NB200_OK) return rc;
+        return rope_pack_dispatch(a.dtype, a.out, a.Mp, a.N, a.norm_q, a.norm_k, a.rotary_emb, a.out_q, a.out_k, a.out_v, a.stride_head_q, a.stride_head_k,
+                                  a.stride_head_v, a.attn_tokens, stream);
+    }
+    if (rope && a.out != nullptr && a.out_q != nullptr) {   // split switched off: the scratch is not needed
+        nb200_gemm_args fused = a;
+        fused.out = nullptr;
+        return pairs == 2 ? launch_cluster<2, hT, EPI_ROPE>(fused, stream) : launch_cluster<1, hT, EPI_ROPE>(fused, stream);
     }
     if (pairs == 2) return rope ? launch_cluster<2, hT, EPI_ROPE>(a, stream) : launch_cluster<2, hT, EPI_DEFAULT>(a, stream);
     return rope ? launch_cluster<1, hT, EPI_ROPE>(a, stream) : launch_cluster<1, hT, EPI_DEFAULT>(a, stream);

@@ -1130,7 +1130,9 @@ extern "C" __attribute__((visibility("default"))) int nb200_gemm_w4a4(const nb20
     if (a->out_q != nullptr || a->out_k != nullptr || a->out_v != nullptr) {
         NB200_REQUIRE(a->rotary_emb != nullptr, "out_q/out_k/out_v are outputs of the RMSNorm+RoPE epilogue (launch_impl:376)");
         NB200_REQUIRE(a->out_q && a->out_k && a->out_v, "out_q, out_k and out_v go together");
-        NB200_REQUIRE(a->out == nullptr, "out and out_q/k/v are exclusive (launch_impl:376-405)");
+        // (the reference writes either `out` or out_q/k/v, launch_impl:376-405; here `out` next to out_q/k/v is an optional [Mp, N] SCRATCH the
+        //  launcher may overwrite: it lets the NVFP4 cluster route run its plain epilogue + the RMSNorm / RoPE / pack kernel of rope.cu)
+        NB200_REQUIRE(a->out == nullptr || (a->M_out == a->Mp && a->N_out == a->N), "with out_q/k/v, out is a scratch of exactly [Mp, N]");
         NB200_REQUIRE(a->attn_tokens >= 0 && a->attn_tokens <= a->Mp, "attn_tokens must be in [0, Mp]");
         NB200_REQUIRE(a->stride_head_q >= static_cast<long long>(a->Mp) * 128 && a->stride_head_k >= static_cast<long long>(a->Mp) * 128 &&
                           a->stride_head_v >= static_cast<long long>(a->Mp) * 128,

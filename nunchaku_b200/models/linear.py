@@ -190,7 +190,10 @@ class SVDQW4A4Linear(nn.Module):
         w = self.b200()
         q, s, la = self.quantize(x2d)
         if out_qkv is not None:
-            gemm_b200(q, s, la, w, act_unsigned=self.act_unsigned, norm_q=norm_q, norm_k=norm_k, rotary_emb=rotary_emb, out_qkv=out_qkv,
+            # NVFP4 at model sizes: a [Mp, N] scratch lets the launcher run the plain GEMM + the RMSNorm / RoPE / pack kernel (csrc/rope.cu)
+            # instead of the fused epilogue -- same bits, faster (include/nunchaku_b200.h: out next to out_q/k/v)
+            scratch = torch.empty(q.shape[0], self.out_features, dtype=w.dtype, device=q.device) if (w.fp4 and q.shape[0] >= 2048) else None
+            gemm_b200(q, s, la, w, out=scratch, act_unsigned=self.act_unsigned, norm_q=norm_q, norm_k=norm_k, rotary_emb=rotary_emb, out_qkv=out_qkv,
                       attn_tokens=attn_tokens)
             return out_qkv
         if output is None:

@@ -194,6 +194,7 @@ def svdq_gemm_w4a4_cuda(
     attn_tokens: int = 0,
     *,
     fuse_gelu: bool = False,
+    qkv_scratch: torch.Tensor | None = None,
 ):
     """Positional/keyword compatible with the reference wrapper (nunchaku/ops/gemm.py:12-160); results are written in place.
     ``fuse_gelu`` (keyword-only extension) applies the reference's tanh-GELU in the plain epilogue.
@@ -230,7 +231,13 @@ def svdq_gemm_w4a4_cuda(
     _require((qout is None) == (oscales is None), "qout and oscales go together")
     _require(out is not None or fused_quant or pack_qkv, "out is required unless qout/oscales or out_q/out_k/out_v are given")
     if pack_qkv:
-        out = None  # the reference ignores `out` in this mode (launch_impl:376-393)
+        # the reference ignores `out` in this mode (launch_impl:376-393); `qkv_scratch` (keyword-only extension: hT [Mp, N], contents unspecified
+        # afterwards) lets the NVFP4 cluster route run the plain GEMM + the RMSNorm / RoPE / pack kernel instead of the fused epilogue
+        out = None
+        if qkv_scratch is not None:
+            _require(qkv_scratch.dim() == 2 and qkv_scratch.shape[0] == act.numel() // act.shape[-1] and qkv_scratch.shape[1] == wgt.shape[0],
+                     "qkv_scratch must be [Mp, N]")
+            out = qkv_scratch
     _require(not fused_quant or smooth_factor is not None, "qout needs smooth_factor (the next layer's smoothing vector)")
     _require((lora_down is None) == (lora_act_out is None), "lora_down and lora_act_out go together (launch_impl:199)")
     if lora_down is not None and not fused_quant:

@@ -183,6 +183,12 @@ def test_qkv_rope_24_heads_full_size(fp4, block_n):
         assert torch.equal(got[:, : c.M].contiguous().view(torch.int16), wantp[part].contiguous().view(torch.int16)), f"part {part}"
         if c.Mp > c.M:
             assert torch.isnan(got[:, c.M:]).all() if part == 1 else bool((got[:, c.M:] == 0).all())
+    # the split route (plain GEMM into a scratch + csrc/rope.cu's RMSNorm / RoPE / pack kernel) writes the same bits
+    outs2 = [torch.full((1, H, c.Mp, 128), 7.0, dtype=torch.float16, device=DEV) for _ in range(3)]
+    scratch = torch.empty(c.Mp, c.N, dtype=hT, device=DEV)
+    run_gemm(c, block_n, out_q=outs2[0], out_k=outs2[1], out_v=outs2[2], attn_tokens=c.M, norm_q=norm_q, norm_k=norm_k, rotary_emb=rot, qkv_scratch=scratch)
+    for part in range(3):
+        assert torch.equal(outs2[part].view(torch.int16), outs[part].view(torch.int16)), f"split route, part {part}"
 
 
 @pytest.mark.parametrize("fp4", [False, True])
