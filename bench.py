@@ -290,11 +290,9 @@ class FullRunner(StackRunner):
         """AdaLayerNormZero(/Single): chunks of the modulation vector, LayerNorm(h) * (1 + scale_msa) + shift_msa"""
         glue = self.glue
         single = self.blocks[i].tag.startswith("single")
-        emb = self.mod[i](glue.silu(self.temb))
+        emb = self.mod[i](self.temb, fuse_silu=True)                 # silu -> W4A16 GEMV -> + bias, one launch
         ch = glue.split_mod(emb.view(1, -1), 3 if single else 6)     # shift_msa, scale_msa, gate_msa[, shift_mlp, scale_mlp, gate_mlp]
-        n = glue.layernorm(h, None, None, 1e-6)
-        glue.mul_add_batch(n.view(1, -1, DIM), ch[1], True, 1.0, ch[0], True)
-        return n, ch
+        return glue.layernorm_mod(h, ch[1], ch[0], 1e-6), ch         # LayerNorm * (1 + scale) + shift, one pass
 
     def _qkv_attn(self, blocks_rows):
         """blocks_rows: [(block, normed input, first row in the joint sequence)] -> attention output rows [T, dim]"""
@@ -318,8 +316,7 @@ class FullRunner(StackRunner):
                 M = b.M
                 o = b.out.forward(attn[rows].reshape(1, M, DIM)).view(M, DIM)
                 glue.mul_add_batch(o.view(1, -1, DIM), ch[2], True, 0.0, h.view(1, -1, DIM), True)        # h + gate_msa * attn_out
-                n2 = glue.layernorm(o, None, None, 1e-6)
-                glue.mul_add_batch(n2.view(1, -1, DIM), ch[4], True, 1.0, ch[3], True)
+                n2 = glue.layernorm_mod(o, ch[4], ch[3], 1e-6)
                 f = b.fc1.forward_mlp(n2, b.fc2, fuse=self.fused._fuse_fc1(b.fc1, M))
                 glue.mul_add_batch(f.view(1, -1, DIM), ch[5], True, 0.0, o.view(1, -1, DIM), True)        # + gate_mlp * ff
                 outs.append(f)

@@ -175,9 +175,17 @@ typedef struct nb200_gemm_args {
     void *out_q, *out_k, *out_v;
     long long stride_head_q, stride_head_k, stride_head_v;
     int attn_tokens;
+    /* fused quantise epilogue with R_down > 0, optional: device scratch of >= nb200_gemm_workspace_bytes(Mp, R_down) bytes whose first
+     * 256-byte-rounded Mp/128 words are ZERO before the first use (the kernel leaves them zero).  With it the per-CTA partial projections of
+     * lora_act_out are reduced in a fixed order by the last CTA to arrive -- identical bits on every launch, no zero-fill of lora_act_out;
+     * without it (NULL / too small) they are added with fp32 atomics like the reference's red.global.add.f32 (lora.cuh:320-353), which is
+     * correct to fp32 rounding but not run-to-run bit-stable.  One workspace per concurrently running launch. */
+    void *workspace;
+    long long workspace_bytes;
 } nb200_gemm_args;
 
 int nb200_gemm_w4a4(const nb200_gemm_args *args, void *stream);
+long long nb200_gemm_workspace_bytes(int Mp, int R_down);
 
 /* ---- elementwise / row-reduce glue between the linears ------------------
  * All tensors contiguous, 16-byte aligned, on the current device; dtype is an nb200_dtype.            */
@@ -190,6 +198,11 @@ int nb200_activation(int kind, int dtype, const void *x, void *out, long long nu
  * Replaces LayerNorm::forward -> layernorm_general (src/layernorm.cpp:14-18, kernels/layernorm_kernels.cu:36-58). */
 int nb200_layernorm(int dtype, const void *x, const void *weight, const void *bias, void *out, long long rows, int hidden,
                     float eps, void *stream);
+/* LayerNorm + AdaLN modulation in one pass: out = LN(x) * (mod_scale[c] + scale_shift) + mod_shift[c] with mod_scale / mod_shift hT [hidden]
+ * (one modulation vector for all rows); same rounding points as nb200_layernorm followed by nb200_mul_add_batch (src/FluxModel.cpp:41-96,
+ * src/kernels/misc_kernels.cu:70-131), i.e. bit-identical, with one read and one write of the activations instead of two. */
+int nb200_layernorm_mod(int dtype, const void *x, const void *weight, const void *bias, const void *mod_scale, const void *mod_shift, float scale_shift,
+                        void *out, long long rows, int hidden, float eps, void *stream);
 
 /* out = T(x * rsqrt(mean(x^2) + eps)) * weight.  Replaces RMSNorm::forward (use_quant = false) -> rms_norm
  * (src/layernorm.cpp:20-24, kernels/layernorm_kernels.cu:6-34).                                          */
@@ -233,6 +246,16 @@ int nb200_linearattn_vk_mul_q(int dtype, void *q, const float *vk, int batch, in
  * out hT [M, OC]; the reference's arithmetic (hT dequant FMA, hT product, fp32 accumulation). */
 int nb200_gemv_awq(int dtype, const void *x, const void *qweight, const void *scales, const void *zeros, void *out, int M, int OC, int IC,
                    int group_size, void *stream);
+/* The same with the two neighbours of the modulation GEMV folded in: x <- silu(x) before the product when
+ * fuse_silu != 0 (kernels::silu, src/kernels/activation_kernels_impl.cuh:7-10) and out += bias (hT [OC], may be NULL) after it -- bit-identical
+ * to the three launches of AdaLayerNormZero::forward (src/FluxModel.cpp:41-96). */
+int nb200_gemv_awq_fused(int dtype, const void *x, const void *qweight, const void *scales, const void *zeros, const void *bias, void *out, int M, int OC,
+                         int IC, int group_size, int fuse_silu, void *stream);
+
+/* ---- SANA GLUMBConv: depthwise 3x3 convolution, NHWC, stride 1, zero padding 1 ---------------------------
+ * Replaces dwconv_f16 (src/kernels/dwconv.h:9, src/kernels/dwconv.cu:202-340; module DWCONV, src/Linear.cpp:541-551).
+ * x / out hT [N, H, W, C] contiguous, weight hT [C, 3, 3] (= the reference's [C, 3, 3, 1]), bias hT [C] or NULL; C % 8 == 0. */
+int nb200_dwconv3x3(int dtype, const void *x, const void *weight, const void *bias, void *out, int N, int H, int W, int C, void *stream);
 
 /* ---- scaled-dot-product attention of the FLUX blocks ------------------------------------------------
  * o[b, i, h*128 + :] = softmax_j(scale * q[b,h,i,:] . k[b,h,j,:]) @ v[b,h,j,:], non-causal, head_dim 128.

@@ -81,6 +81,8 @@ class GemmArgs(ctypes.Structure):
         ("stride_head_k", c_longlong),
         ("stride_head_v", c_longlong),
         ("attn_tokens", c_int),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_longlong),
     ]
 
 
@@ -102,6 +104,7 @@ SYMBOLS = {
     "nb200_gemm_w4a4": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "nb200_activation": (c_int, [c_int, c_int, c_void_p, c_void_p, c_longlong, c_void_p]),
     "nb200_layernorm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
+    "nb200_layernorm_mod": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "nb200_rms_norm": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_void_p]),
     "nb200_add": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "nb200_mul_add_batch": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_float, c_int, c_longlong, c_longlong, c_longlong,
@@ -112,6 +115,9 @@ SYMBOLS = {
     "nb200_linearattn_vk_mul_q": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "nb200_attention_fp16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "nb200_gemv_awq": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "nb200_gemm_workspace_bytes": (c_longlong, [c_int, c_int]),
+    "nb200_dwconv3x3": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "nb200_gemv_awq_fused": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 

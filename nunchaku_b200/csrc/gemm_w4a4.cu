@@ -68,6 +68,8 @@ struct GemmParams {
     float *lora_act_out;     // [Mp][R_down], pre-zeroed
     int R_down, Rdp;
     int tile_contig;         // 1: each CTA owns a contiguous range of tiles (same m-block runs), see EPI_QUANT
+    float *ws_partial;       // EPI_QUANT, optional: [m-block + CTA][128 rows][Rdp] partial down projections (deterministic reduction) or null
+    unsigned int *ws_ticket; // [m-blocks], zero between launches (self-cleaning)
     // EPI_ROPE
     const void *norm_q, *norm_k;  // hT [128]
     const float *rotary;          // reference pack_rotemb layout [Mp][128]
@@ -83,6 +85,8 @@ struct GemmParams {
 
 enum { EPI_DEFAULT = 0, EPI_QUANT = 1, EPI_ROPE = 2 };
 constexpr int kMaxRdp = 128;  // largest fused next-layer rank (smem / TMEM budget)
+constexpr int kWsMaxCtas = 256;  // runs the deterministic-reduction workspace is sized for (one CTA per SM)
+inline long long kWsTicketBytes(int Mp) { return ((static_cast<long long>(Mp / 128) * 4 + 255) / 256) * 256; }
 
 template <bool FP4, int BN, int EPI = EPI_DEFAULT>
 struct Cfg {
@@ -160,6 +164,7 @@ struct alignas(1024) Smem {
     uint64_t stage_mma_done[2];
     uint64_t d2_full;
     uint32_t tmem_base;
+    uint32_t d2_is_last;
 };
 
 // cycle accounting of the barrier waits (written out only when p.prof != nullptr)
@@ -886,16 +891,69 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         d2_phase ^= 1;
                         tc_fence_after_sync();
                         float *dst = p.lora_act_out + static_cast<size_t>(m0 + row) * p.R_down;
-                        // two groups: each adds half of the 16-rank column blocks
-                        for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
-                            uint32_t d2[16];
-                            tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kTmemLd + c16 * 16, d2);
-                            tmem_ld_wait();
+                        if (p.ws_partial != nullptr) {
+                            // Deterministic reduction (the reference adds its partials with red.global.add.f32, launch_impl:252 +
+                            // lora.cuh:320-353): this CTA's run of the m-block goes to workspace slot mb + blockIdx.x (runs ordered by (m-block, CTA)
+                            // form a staircase, so the sum is unique per run); the LAST run to arrive (ticket) adds all of the m-block's runs in
+                            // CTA order and stores the result -- lora_act_out needs no zero-fill and every launch gives the same bits.
+                            float *mine = p.ws_partial + (static_cast<size_t>(mb + blockIdx.x) * BM + row) * p.Rdp;
+                            for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
+                                uint32_t d2[16];
+                                tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kTmemLd + c16 * 16, d2);
+                                tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 16; i++)
-                                if (c16 * 16 + i < p.R_down && !(p.debug & 16)) atomicAdd(dst + c16 * 16 + i, __uint_as_float(d2[i]));
+                                for (int i = 0; i < 16; i += 4)
+                                    __stcg(reinterpret_cast<float4 *>(mine + c16 * 16 + i), make_float4(__uint_as_float(d2[i]), __uint_as_float(d2[i + 1]),
+                                                                                                        __uint_as_float(d2[i + 2]), __uint_as_float(d2[i + 3])));
+                            }
+                            tc_fence_before_sync();
+                            __threadfence();
+                            named_bar_sync(1, C::kEpiThreads);
+                            // CTAs whose tile range touches this m-block: owner(t) = ceil((t + 1) * grid / tiles) - 1
+                            const long long t_first = static_cast<long long>(mb) * p.num_n_blocks, t_last = t_first + p.num_n_blocks - 1;
+                            const int b_first = static_cast<int>(((t_first + 1) * gridDim.x + p.num_tiles - 1) / p.num_tiles) - 1;
+                            const int b_last = static_cast<int>(((t_last + 1) * gridDim.x + p.num_tiles - 1) / p.num_tiles) - 1;
+                            if (eta == 0) {
+                                const unsigned int ticket = atomicAdd(&p.ws_ticket[mb], 1u);
+                                const bool last = ticket == static_cast<unsigned int>(b_last - b_first);
+                                if (last) p.ws_ticket[mb] = 0;   // self-cleaning for the next launch
+                                s.d2_is_last = last ? 1u : 0u;
+                            }
+                            named_bar_sync(1, C::kEpiThreads);
+                            if (s.d2_is_last) {
+                                __threadfence();
+                                for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
+                                    float acc16[16];
+#pragma unroll
+                                    for (int i = 0; i < 16; i++) acc16[i] = 0.f;
+                                    for (int b = b_first; b <= b_last; b++) {
+                                        const float *src = p.ws_partial + (static_cast<size_t>(mb + b) * BM + row) * p.Rdp + c16 * 16;
+#pragma unroll
+                                        for (int i = 0; i < 16; i += 4) {
+                                            const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + i));
+                                            acc16[i] += v.x;
+                                            acc16[i + 1] += v.y;
+                                            acc16[i + 2] += v.z;
+                                            acc16[i + 3] += v.w;
+                                        }
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < 16; i++)
+                                        if (c16 * 16 + i < p.R_down) dst[c16 * 16 + i] = acc16[i];
+                                }
+                            }
+                        } else {
+                            // two groups: each adds half of the 16-rank column blocks
+                            for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
+                                uint32_t d2[16];
+                                tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kTmemLd + c16 * 16, d2);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 16; i++)
+                                    if (c16 * 16 + i < p.R_down && !(p.debug & 16)) atomicAdd(dst + c16 * 16 + i, __uint_as_float(d2[i]));
+                            }
+                            tc_fence_before_sync();
                         }
-                        tc_fence_before_sync();
                     }
                 }
             }
@@ -999,7 +1057,9 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
         rc = make_map_2d(&tm_ld, odt, a.lora_down_next, a.N, rdp, static_cast<uint64_t>(a.N) * 2, 64, rdp,
                          CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
-        NB200_CUDA_CHECK(cudaMemsetAsync(a.lora_act_out, 0, static_cast<size_t>(a.Mp) * a.R_down * sizeof(float), stream));
+        // without a workspace the partial projections are ADDED to lora_act_out with fp32 atomics: zero it first (as the reference does, launch_impl:252)
+        if (a.workspace == nullptr || a.workspace_bytes < nb200_gemm_workspace_bytes(a.Mp, a.R_down))
+            NB200_CUDA_CHECK(cudaMemsetAsync(a.lora_act_out, 0, static_cast<size_t>(a.Mp) * a.R_down * sizeof(float), stream));
     } else {
         tm_ld = tm_act;
     }
@@ -1035,6 +1095,12 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.lora_act_out = a.lora_act_out;
     p.R_down = a.R_down;
     p.Rdp = rdp;
+    p.ws_partial = nullptr;
+    p.ws_ticket = nullptr;
+    if (EPI == EPI_QUANT && a.R_down > 0 && a.workspace != nullptr && a.workspace_bytes >= nb200_gemm_workspace_bytes(a.Mp, a.R_down)) {
+        p.ws_ticket = static_cast<unsigned int *>(a.workspace);
+        p.ws_partial = reinterpret_cast<float *>(static_cast<uint8_t *>(a.workspace) + kWsTicketBytes(a.Mp));
+    }
     p.norm_q = a.norm_q;
     p.norm_k = a.norm_k;
     p.rotary = a.rotary_emb;
@@ -1051,6 +1117,9 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     if (int rc2 = current_device_sms(&num_sms_dev)) return rc2;
     const int num_sms = a.num_sms > 0 ? a.num_sms : num_sms_dev;
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    if (grid > kWsMaxCtas) p.ws_partial = nullptr;   // (the workspace is sized for kWsMaxCtas runs; p.ws_partial == nullptr selects the atomics)
+    if (EPI == EPI_QUANT && a.R_down > 0 && p.ws_partial == nullptr && a.workspace != nullptr && a.workspace_bytes >= nb200_gemm_workspace_bytes(a.Mp, a.R_down))
+        NB200_CUDA_CHECK(cudaMemsetAsync(a.lora_act_out, 0, static_cast<size_t>(a.Mp) * a.R_down * sizeof(float), stream));
     const size_t smem_bytes = sizeof(S) + 1024;
     auto kern = gemm_w4a4_kernel<FP4, hT, BN, EPI>;
     if (int rc2 = set_max_smem_once(reinterpret_cast<const void *>(kern), smem_bytes)) return rc2;
@@ -1099,6 +1168,13 @@ int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
 
 }  // namespace
 }  // namespace nb200
+
+// ticket area (one u32 per 128-row block, rounded to 256 B, ZERO before the first use, self-cleaning afterwards) + one [128][R_down] fp32 slot
+// per (m-block, CTA) run
+extern "C" __attribute__((visibility("default"))) long long nb200_gemm_workspace_bytes(int Mp, int R_down) {
+    if (Mp <= 0 || R_down <= 0) return 0;
+    return nb200::kWsTicketBytes(Mp) + (static_cast<long long>(Mp / 128) + nb200::kWsMaxCtas) * 128 * R_down * 4;
+}
 
 extern "C" __attribute__((visibility("default"))) int nb200_gemm_w4a4(const nb200_gemm_args *a, void *stream_) {
     using namespace nb200;

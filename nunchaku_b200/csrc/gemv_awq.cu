@@ -25,16 +25,31 @@ constexpr int kWarps = 8;            // 8 groups of 4 output channels per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxM = 8;
 
-template <typename hT, int M>
+// FUSE_SILU: x <- silu(x) while it is staged (the modulation linears see silu(temb): src/FluxModel.cpp AdaLayerNormZero::forward runs
+// kernels::silu first) with the activation kernel's arithmetic (x / (1 + expf(-x)) in fp32, one rounding: activation_kernels_impl.cuh:7-10);
+// bias: added to the rounded result in hT like the caller's `out += bias` -- both bit-identical to the separate launches they replace.
+template <typename hT, int M, bool FUSE_SILU>
 __global__ void __launch_bounds__(kThreads) gemv_awq_kernel(const hT *__restrict__ x, const uint4 *__restrict__ qw, const hT *__restrict__ scales,
-                                                            const hT *__restrict__ zeros, hT *__restrict__ out, int OC, int IC) {
+                                                            const hT *__restrict__ zeros, const hT *__restrict__ bias, hT *__restrict__ out, int OC,
+                                                            int IC) {
     using Tr = HalfTraits<hT>;
     using T2 = typename Tr::T2;
     extern __shared__ uint4 xs4[];   // [M][IC] hT
     ptx::griddep_launch_dependents();
     ptx::griddep_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < M * IC / 8; i += kThreads) xs4[i] = reinterpret_cast<const uint4 *>(x)[i];
+    for (int i = threadIdx.x; i < M * IC / 8; i += kThreads) {
+        uint4 v = reinterpret_cast<const uint4 *>(x)[i];
+        if constexpr (FUSE_SILU) {
+            hT *e = reinterpret_cast<hT *>(&v);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float f = Tr::to_float(e[k]);
+                e[k] = Tr::from_float(f / (1.0f + expf(-f)));
+            }
+        }
+        xs4[i] = v;
+    }
     __syncthreads();
     const int group = blockIdx.x * kWarps + warp;    // 4 output channels
     if (group * 4 >= OC) return;
@@ -101,22 +116,27 @@ __global__ void __launch_bounds__(kThreads) gemv_awq_kernel(const hT *__restrict
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (h == 0 && c == 0) out[static_cast<size_t>(m) * OC + oc] = Tr::from_float(v);
+        if (h == 0 && c == 0) {
+            hT y = Tr::from_float(v);
+            if (bias != nullptr) y = Tr::from_float(Tr::to_float(y) + Tr::to_float(bias[oc]));
+            out[static_cast<size_t>(m) * OC + oc] = y;
+        }
     }
 }
 
-template <typename hT>
-int launch_gemv(const void *x, const void *qw, const void *scales, const void *zeros, void *out, int M, int OC, int IC, cudaStream_t stream) {
+template <typename hT, bool FUSE_SILU>
+int launch_gemv(const void *x, const void *qw, const void *scales, const void *zeros, const void *bias, void *out, int M, int OC, int IC,
+                cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(M) * IC * sizeof(hT);
     const int grid = (OC / 4 + kWarps - 1) / kWarps;
 #define NB200_GEMV_CASE(MM)                                                                                                                        \
     case MM: {                                                                                                                                     \
-        auto kern = gemv_awq_kernel<hT, MM>;                                                                                                       \
+        auto kern = gemv_awq_kernel<hT, MM, FUSE_SILU>;                                                                                                       \
         if (smem > 48 * 1024)                                                                                                                      \
             if (int rc = set_max_smem_once(reinterpret_cast<const void *>(kern), smem)) return rc;                                                 \
         LaunchCfg lc(dim3(grid), dim3(kThreads), smem, stream);                                                                                    \
         NB200_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, static_cast<const hT *>(x), static_cast<const uint4 *>(qw), static_cast<const hT *>(scales), \
-                                            static_cast<const hT *>(zeros), static_cast<hT *>(out), OC, IC));                                      \
+                                            static_cast<const hT *>(zeros), static_cast<const hT *>(bias), static_cast<hT *>(out), OC, IC));       \
         break;                                                                                                                                     \
     }
     switch (M) {
@@ -138,8 +158,10 @@ int launch_gemv(const void *x, const void *qw, const void *scales, const void *z
 }  // namespace
 }  // namespace nb200
 
-extern "C" __attribute__((visibility("default"))) int nb200_gemv_awq(int dtype, const void *x, const void *qweight, const void *scales, const void *zeros,
-                                                                     void *out, int M, int OC, int IC, int group_size, void *stream_) {
+// bias (hT [OC]) may be NULL; fuse_silu != 0 applies SiLU to x first (the AdaLN modulation path: silu -> gemv -> + bias in one launch)
+extern "C" __attribute__((visibility("default"))) int nb200_gemv_awq_fused(int dtype, const void *x, const void *qweight, const void *scales,
+                                                                           const void *zeros, const void *bias, void *out, int M, int OC, int IC,
+                                                                           int group_size, int fuse_silu, void *stream_) {
     using namespace nb200;
     reset_launch_count();
     NB200_REQUIRE(x && qweight && scales && zeros && out, "NULL tensor");
@@ -151,6 +173,14 @@ extern "C" __attribute__((visibility("default"))) int nb200_gemv_awq(int dtype, 
     NB200_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(qweight)) & 15) == 0, "x / qweight must be 16-byte aligned");
     NB200_REQUIRE(static_cast<size_t>(M) * IC * 2 <= 200 * 1024, "M * IC does not fit shared memory");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    return dtype == NB200_BF16 ? launch_gemv<__nv_bfloat16>(x, qweight, scales, zeros, out, M, OC, IC, stream)
-                               : launch_gemv<__half>(x, qweight, scales, zeros, out, M, OC, IC, stream);
+    if (dtype == NB200_BF16)
+        return fuse_silu ? launch_gemv<__nv_bfloat16, true>(x, qweight, scales, zeros, bias, out, M, OC, IC, stream)
+                         : launch_gemv<__nv_bfloat16, false>(x, qweight, scales, zeros, bias, out, M, OC, IC, stream);
+    return fuse_silu ? launch_gemv<__half, true>(x, qweight, scales, zeros, bias, out, M, OC, IC, stream)
+                     : launch_gemv<__half, false>(x, qweight, scales, zeros, bias, out, M, OC, IC, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int nb200_gemv_awq(int dtype, const void *x, const void *qweight, const void *scales, const void *zeros,
+                                                                     void *out, int M, int OC, int IC, int group_size, void *stream_) {
+    return nb200_gemv_awq_fused(dtype, x, qweight, scales, zeros, nullptr, out, M, OC, IC, group_size, 0, stream_);
 }

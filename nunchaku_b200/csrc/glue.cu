@@ -299,7 +299,8 @@ norm_kernel(const T *__restrict__ x, const T *__restrict__ gamma, const T *__res
 template <typename T, bool RMS, int MAXC>
 __global__ void __launch_bounds__(kThreads)
 norm_warp_kernel(const T *__restrict__ x, const T *__restrict__ gamma, const T *__restrict__ beta, T *__restrict__ out,
-                 long long rows, int hidden, float eps) {
+                 long long rows, int hidden, float eps, const T *__restrict__ mod_scale = nullptr, const T *__restrict__ mod_shift = nullptr,
+                 float mod_scale_shift = 0.f) {
     constexpr int V = 8;
     const int lane = threadIdx.x & 31;
     const long long row = static_cast<long long>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5);
@@ -356,6 +357,12 @@ norm_warp_kernel(const T *__restrict__ x, const T *__restrict__ gamma, const T *
                     if (beta != nullptr) r = r + to_f(b.v[k]);
                     a.v[k] = from_f<T>(r);
                 }
+            }
+            if (mod_shift != nullptr) {   // AdaLN: the mul_add kernel's arithmetic on the rounded norm (nb200_layernorm_mod): y * (scale + c) + shift in T
+                const Vec<T, V> ms = reinterpret_cast<const Vec<T, V> *>(mod_scale)[j], mb = reinterpret_cast<const Vec<T, V> *>(mod_shift)[j];
+                const T c = from_f<T>(mod_scale_shift);
+#pragma unroll
+                for (int k = 0; k < V; k++) a.v[k] = clamp_half(t_add(t_mul(a.v[k], t_add(ms.v[k], c)), mb.v[k]));
             }
             reinterpret_cast<Vec<T, V> *>(orow)[j] = a;
         }
@@ -573,6 +580,43 @@ static int launch_norm(bool rms, int dtype, const void *x, const void *weight, c
 int nb200_layernorm(int dtype, const void *x, const void *weight, const void *bias, void *out, long long rows, int hidden,
                     float eps, void *stream) {
     return launch_norm(false, dtype, x, weight, bias, out, rows, hidden, eps, static_cast<cudaStream_t>(stream));
+}
+
+// LayerNorm followed by the AdaLN modulation  y * (mod_scale[c] + scale_shift) + mod_shift[c]  in ONE pass over the rows (SURVEY section 8f row N2:
+// the reference runs layernorm + mul_add_batch, src/FluxModel.cpp AdaLayerNormZero::forward); bit-identical to nb200_layernorm followed by
+// nb200_mul_add_batch (same rounding points), one read + one write of the activations instead of two.
+int nb200_layernorm_mod(int dtype, const void *x, const void *weight, const void *bias, const void *mod_scale, const void *mod_shift, float scale_shift,
+                        void *out, long long rows, int hidden, float eps, void *stream_) {
+    reset_launch_count();
+    NB200_REQUIRE(x && out && mod_scale && mod_shift, "NULL tensor");
+    NB200_REQUIRE(rows >= 0 && hidden > 0 && hidden % 8 == 0, "hidden must be a positive multiple of 8");
+    NB200_REQUIRE(dtype == NB200_FP16 || dtype == NB200_BF16, "dtype must be fp16 or bf16");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (rows == 0) return NB200_OK;
+    if (hidden > 4096) {   // rows too long for the one-warp-per-row kernel: the two launches
+        if (int rc = launch_norm(false, dtype, x, weight, bias, out, rows, hidden, eps, stream)) return rc;
+        return nb200_mul_add_batch(dtype, out, mod_scale, mod_shift, scale_shift, 1, rows * hidden, hidden, hidden, 0, 0, 0, stream_);
+    }
+    const int wgrid = static_cast<int>((rows + kThreads / 32 - 1) / (kThreads / 32));
+    const int wc = (hidden / 8 + 31) / 32;
+    auto go = [&](auto tag) {
+        using T = decltype(tag);
+        const T *xp = static_cast<const T *>(x), *g = static_cast<const T *>(weight), *b = static_cast<const T *>(bias);
+        const T *ms = static_cast<const T *>(mod_scale), *mb = static_cast<const T *>(mod_shift);
+        T *o = static_cast<T *>(out);
+#define NB200_NORMW(C) norm_warp_kernel<T, false, C><<<wgrid, kThreads, 0, stream>>>(xp, g, b, o, rows, hidden, eps, ms, mb, scale_shift)
+        if (wc <= 1) NB200_NORMW(1);
+        else if (wc <= 4) NB200_NORMW(4);
+        else if (wc <= 8) NB200_NORMW(8);
+        else if (wc <= 12) NB200_NORMW(12);
+        else NB200_NORMW(16);
+#undef NB200_NORMW
+    };
+    if (dtype == NB200_BF16) go(__nv_bfloat16{});
+    else go(__half{});
+    NB200_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return NB200_OK;
 }
 
 int nb200_rms_norm(int dtype, const void *x, const void *weight, void *out, long long rows, int hidden, float eps, void *stream) {

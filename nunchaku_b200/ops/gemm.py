@@ -105,6 +105,8 @@ def _launch(c: _Call) -> None:
             lo = c.lora_act_out
             _require(lo.dtype == torch.float32 and lo.is_contiguous() and tuple(lo.shape) == (Mp, c.rank_down), "lora_act_out must be float32 [Mp, rank]")
             args.lora_down_next, args.lora_act_out, args.R_down = c.lora_down_next.data_ptr(), lo.data_ptr(), c.rank_down
+            ws = _reduce_workspace(Mp, c.rank_down, c.act.device)      # deterministic reduction of the per-CTA partial projections
+            args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
     keep = []
     if c.rotary_emb is not None:
         rot = c.rotary_emb
@@ -296,6 +298,20 @@ def linearattn_vk_mul_q(q: torch.Tensor, vk: torch.Tensor) -> None:
         raise ValueError("q must be contiguous [B, tokens, heads * 32]")
     check(lib.nb200_linearattn_vk_mul_q(torch_dtype_code(q.dtype), q.data_ptr(), vk.data_ptr(), B, q.shape[1], heads, 1e-6,
                                         torch.cuda.current_stream().cuda_stream), "linearattn_vk_mul_q")
+
+
+_ws_cache: dict[tuple, torch.Tensor] = {}
+
+
+def _reduce_workspace(Mp: int, rank: int, device) -> torch.Tensor:
+    """Scratch of the fused quantise epilogue's deterministic reduction (include/nunchaku_b200.h: nb200_gemm_args.workspace), one per
+    (device, stream, size): zero-initialised once, the kernel keeps its ticket words zero."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream, Mp, rank)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.nb200_gemm_workspace_bytes(Mp, rank)), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
 
 
 _const_cache: dict[tuple, torch.Tensor] = {}

@@ -11,9 +11,11 @@ from ..utils import on_device_of, torch_dtype_code
 
 @on_device_of("in_feats")
 def awq_gemv_w4a16_cuda(in_feats: torch.Tensor, kernel: torch.Tensor, scaling_factors: torch.Tensor, zeros: torch.Tensor, m: int, n: int, k: int,
-                        group_size: int = 64) -> torch.Tensor:
+                        group_size: int = 64, *, bias: torch.Tensor | None = None, fuse_silu: bool = False) -> torch.Tensor:
     """``in_feats`` (k,) or (m, k) hT; ``kernel`` int32 (n // 4, k // 2) in the checkpoint layout (read in place); ``scaling_factors`` /
-    ``zeros`` hT (k // group_size, n).  Returns (m, n) hT [(n,) for a 1-D input]."""
+    ``zeros`` hT (k // group_size, n).  Returns (m, n) hT [(n,) for a 1-D input].  Keyword-only extensions (SURVEY row N2): ``bias`` (n,) is
+    added in the kernel's epilogue, ``fuse_silu`` applies SiLU to the input first -- the AdaLN modulation's silu -> gemv -> + bias as ONE launch,
+    bit-identical to the three."""
     if not in_feats.is_cuda:
         raise RuntimeError("nunchaku_b200 has no CPU path: in_feats must be a CUDA tensor")
     x = in_feats.contiguous().view(-1, k)
@@ -24,9 +26,12 @@ def awq_gemv_w4a16_cuda(in_feats: torch.Tensor, kernel: torch.Tensor, scaling_fa
     for t in (scaling_factors, zeros):
         if t.dtype != x.dtype or tuple(t.shape) != (k // group_size, n) or not t.is_contiguous():
             raise ValueError("scaling_factors / zeros must be contiguous (k // group_size, n) tensors of the input dtype")
+    if bias is not None and (bias.dtype != x.dtype or bias.numel() != n or not bias.is_contiguous()):
+        raise ValueError("bias must be a contiguous (n,) tensor of the input dtype")
     out = torch.empty(m, n, dtype=x.dtype, device=x.device)
-    check(lib.nb200_gemv_awq(torch_dtype_code(x.dtype), x.data_ptr(), kernel.data_ptr(), scaling_factors.data_ptr(), zeros.data_ptr(), out.data_ptr(),
-                             m, n, k, group_size, torch.cuda.current_stream().cuda_stream), "gemv_awq")
+    check(lib.nb200_gemv_awq_fused(torch_dtype_code(x.dtype), x.data_ptr(), kernel.data_ptr(), scaling_factors.data_ptr(), zeros.data_ptr(),
+                                   None if bias is None else bias.data_ptr(), out.data_ptr(), m, n, k, group_size, int(bool(fuse_silu)),
+                                   torch.cuda.current_stream().cuda_stream), "gemv_awq")
     return out.view(n) if in_feats.dim() == 1 else out
 
 
@@ -48,9 +53,10 @@ class AWQW4A16Linear(nn.Module):
     def from_linear(cls, linear: nn.Linear, group_size: int = 64, torch_dtype: torch.dtype = torch.bfloat16, device="cpu", **_):
         return cls(linear.in_features, linear.out_features, bias=linear.bias is not None, group_size=group_size, torch_dtype=torch_dtype, device=device)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = awq_gemv_w4a16_cuda(x, self.qweight, self.wscales, self.wzeros, x.shape[0], self.out_features, self.in_features, self.group_size)
-        return y if self.bias is None else y.add_(self.bias)
+    def forward(self, x: torch.Tensor, *, fuse_silu: bool = False) -> torch.Tensor:
+        """``fuse_silu``: y = W silu(x) + b in one launch (what AdaLayerNormZero does with three, src/FluxModel.cpp:41-96)"""
+        return awq_gemv_w4a16_cuda(x, self.qweight, self.wscales, self.wzeros, x.shape[0], self.out_features, self.in_features, self.group_size,
+                                   bias=self.bias, fuse_silu=fuse_silu)
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, group_size={self.group_size}"

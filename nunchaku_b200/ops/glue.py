@@ -73,6 +73,24 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor | None = None, bias: torch.T
     return out
 
 
+def layernorm_mod(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, eps: float = 1e-6, *, scale_shift: float = 1.0,
+                  weight: torch.Tensor | None = None, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """AdaLN in one pass over the activations: ``LayerNorm(x) * (scale + scale_shift) + shift`` with one modulation vector
+    (``scale`` / ``shift``: ``hidden`` elements) for all rows -- what the reference's AdaLayerNormZero does as ``layernorm`` followed by
+    ``mul_add_batch(norm, scale, True, 1.0, shift, True)`` (src/FluxModel.cpp:41-96); same rounding points, bit-identical result."""
+    _cuda(x, scale, shift, weight, bias)
+    x = x.contiguous()
+    hidden = x.shape[-1]
+    for p in (scale, shift, weight, bias):
+        if p is not None and (p.dtype != x.dtype or p.numel() != hidden or not p.is_contiguous()):
+            raise ValueError("scale / shift / weight / bias must be contiguous tensors of hidden elements and x's dtype")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.nb200_layernorm_mod(_code(x), x.data_ptr(), _ptr(weight), _ptr(bias), scale.data_ptr(), shift.data_ptr(), float(scale_shift),
+                                      out.data_ptr(), x.numel() // hidden if hidden else 0, hidden, float(eps), _stream()), "nb200_layernorm_mod")
+    return out
+
+
 def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     """``RMSNorm::forward`` with ``use_quant = false`` (src/layernorm.cpp:20-24)."""
     _cuda(x, weight)

@@ -52,7 +52,7 @@ def test_struct_layout_matches_header_sizes():
     from nunchaku_b200._C import GemmArgs, QuantizeArgs
 
     assert ctypes.sizeof(QuantizeArgs) == 104
-    assert ctypes.sizeof(GemmArgs) == 512
+    assert ctypes.sizeof(GemmArgs) == 528
 
 
 def test_struct_layout_matches_a_c_compiler(tmp_path):

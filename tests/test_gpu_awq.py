@@ -102,3 +102,22 @@ def test_gemv_awq_through_the_cpp_seam_and_the_pybind_surface():
         C = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(C)
         assert torch.equal(C.ops.gemv_awq(x, qw, sc, ze, m, OC, IC, 64), y)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_gemv_fused_silu_bias_equals_three_launches(dt):
+    """silu -> gemv -> + bias as one launch (nb200_gemv_awq_fused) == the three separate launches, bit for bit"""
+    from nunchaku_b200.ops import glue
+    from nunchaku_b200.ops.gemv import awq_gemv_w4a16_cuda
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    IC, OC = 3072, 18432
+    x = torch.randn(1, IC, generator=g, device="cuda").to(dt)
+    qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (OC // 4, IC // 2), generator=g, device="cuda", dtype=torch.int64).to(torch.int32)
+    sc = (0.01 + 0.01 * torch.rand(IC // 64, OC, generator=g, device="cuda")).to(dt)
+    zr = (-0.08 * torch.rand(IC // 64, OC, generator=g, device="cuda")).to(dt)
+    bias = (0.1 * torch.randn(OC, generator=g, device="cuda")).to(dt)
+    want = awq_gemv_w4a16_cuda(glue.silu(x), qw, sc, zr, 1, OC, IC).add_(bias)
+    got = awq_gemv_w4a16_cuda(x, qw, sc, zr, 1, OC, IC, bias=bias, fuse_silu=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))

@@ -382,3 +382,51 @@ def test_qkv_rmsnorm_rope_cluster_kernel(hT, block_n, H):
         got = outs[part][0].cpu()
         assert torch.equal(got[:, :M].view(torch.int16), want[part][:, :M].view(torch.int16)), f"part {part}"
         assert torch.isnan(got[:, M:]).all() if part == 1 else bool((got[:, M:] == 0).all())
+
+
+@pytest.mark.parametrize("precision", ["nvfp4", "int4"])
+@pytest.mark.parametrize("M,D,H", [(300, 256, 512), (256, 3072, 12288)])
+def test_fused_handoff_is_bit_stable(precision, M, D, H):
+    """The fused fc1 epilogue's low-rank hidden state for fc2 is a sum over CTAs (several CTAs share a 128-row block, one CTA may span two): with
+    the reduction workspace the partials are added in a fixed order by the last CTA to arrive, so repeated launches give identical bits
+    (the reference adds them with red.global.add.f32) -- and they agree with the atomics path to fp32 rounding."""
+    from nunchaku_b200.models.linear import SVDQW4A4Linear
+    from nunchaku_b200.ops import gemm as G
+
+    hT = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+
+    def mk(K, N, unsigned):
+        m = SVDQW4A4Linear(K, N, rank=32, bias=True, precision=precision, act_unsigned=unsigned, torch_dtype=hT, device="cuda")
+        with torch.no_grad():
+            m.qweight.copy_(torch.randint(-128, 128, m.qweight.shape, generator=g, device="cuda", dtype=torch.int8))
+            if precision == "nvfp4":
+                m.wscales.copy_(torch.randint(0x30, 0x38, m.wscales.shape, generator=g, device="cuda", dtype=torch.uint8).view(torch.float8_e4m3fn))
+                m.wtscale = 1.0 / (2.6 * 0.72 * K ** 0.5)
+                m.wcscales.copy_((1.0 + 0.05 * torch.randn(N, generator=g, device="cuda")).to(hT))
+            else:
+                m.wscales.copy_(((0.75 + 0.5 * torch.rand(m.wscales.shape, generator=g, device="cuda")) / (4.6 * K ** 0.5)).to(hT))
+            m.bias.copy_((0.1 * torch.randn(N, generator=g, device="cuda")).to(hT))
+            m.smooth_factor.copy_((0.75 + 0.5 * torch.rand(K, generator=g, device="cuda")).to(hT))
+            m.proj_down.copy_((torch.randn(K, 32, generator=g, device="cuda") / K ** 0.5).to(hT))
+            m.proj_up.copy_((0.1 * torch.randn(N, 32, generator=g, device="cuda") / 32 ** 0.5).to(hT))
+        m.invalidate()
+        return m
+
+    fc1, fc2 = mk(D, H, False), mk(H, D, precision == "int4")
+    x = torch.randn(M, D, generator=g, device="cuda").to(hT)
+    q, s, la = fc1.quantize(x)
+    runs = [fc1.quantize_next(q, s, la, fc2) for _ in range(4)]
+    torch.cuda.synchronize()
+    for q2, s2, la2 in runs[1:]:
+        assert torch.equal(la2.view(torch.int32), runs[0][2].view(torch.int32))
+        assert torch.equal(q2, runs[0][0]) and torch.equal(s2.view(torch.uint8), runs[0][1].view(torch.uint8))
+    # the atomics path (no workspace) sums the same partials in a different order
+    orig = G._reduce_workspace
+    G._reduce_workspace = lambda Mp, rank, device: torch.zeros(0, dtype=torch.uint8, device=device)
+    try:
+        la_atomic = fc1.quantize_next(q, s, la, fc2)[2]
+    finally:
+        G._reduce_workspace = orig
+    torch.cuda.synchronize()
+    assert O.rel_fro(la_atomic.cpu(), runs[0][2].cpu()) <= 1e-6

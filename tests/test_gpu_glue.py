@@ -172,3 +172,20 @@ def test_preconditions():
         glue.add(x, x[:2])
     with pytest.raises(RuntimeError):
         glue.layernorm(torch.randn(4, 12, device="cuda", dtype=torch.bfloat16))  # hidden % 8 != 0
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,hidden", [(300, 3072), (17, 2240), (5, 8192)])
+def test_layernorm_mod_equals_layernorm_then_mul_add(dt, rows, hidden):
+    """AdaLN in one pass (nb200_layernorm_mod) == layernorm followed by mul_add_batch, bit for bit"""
+    from nunchaku_b200.ops import glue
+
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = (torch.randn(1, rows, hidden, generator=g, device="cuda") * 3 + 0.5).to(dt)
+    scale = (0.3 * torch.randn(1, hidden, generator=g, device="cuda")).to(dt)
+    shift = (0.3 * torch.randn(1, hidden, generator=g, device="cuda")).to(dt)
+    want = glue.layernorm(x, None, None, 1e-6)
+    glue.mul_add_batch(want, scale, True, 1.0, shift, True)
+    got = glue.layernorm_mod(x, scale, shift, 1e-6)
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
