@@ -96,3 +96,38 @@ def test_on_device_of_passes_through_and_preserves_signature():
     params = inspect.signature(svdq_gemm_w4a4_cuda).parameters
     assert list(params)[:5] == ["act", "wgt", "out", "qout", "ascales"] and list(params)[28] == "attn_tokens"
     assert params["fuse_gelu"].kind is inspect.Parameter.KEYWORD_ONLY
+
+
+def test_round2_ops_reject_cpu_tensors_and_keep_reference_signatures():
+    """attention / AWQ GEMV / depthwise conv / AdaLN glue / graph capture: errors on CPU, never a fallback; reference argument order kept."""
+    import inspect
+
+    from nunchaku_b200.graph import GraphedStep
+    from nunchaku_b200.ops.attention import attention_fp16
+    from nunchaku_b200.ops.dwconv import DWCONV, dwconv_f16
+    from nunchaku_b200.ops.gemv import AWQW4A16Linear, awq_gemv_w4a16_cuda
+
+    q = torch.zeros(1, 2, 128, 128, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        attention_fp16(q, q, q, torch.zeros(1, 128, 256, dtype=torch.float16), 0.1)
+    assert list(inspect.signature(attention_fp16).parameters) == ["q", "k", "v", "o", "scale"]          # _C.ops.attention_fp16 (csrc/ops.h)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        awq_gemv_w4a16_cuda(torch.zeros(1, 256, dtype=torch.bfloat16), torch.zeros(2, 128, dtype=torch.int32), torch.zeros(4, 8, dtype=torch.bfloat16),
+                            torch.zeros(4, 8, dtype=torch.bfloat16), 1, 8, 256)
+    p = inspect.signature(awq_gemv_w4a16_cuda).parameters
+    assert list(p)[:8] == ["in_feats", "kernel", "scaling_factors", "zeros", "m", "n", "k", "group_size"]  # nunchaku/ops/gemv.py:10-58
+    assert p["bias"].kind is inspect.Parameter.KEYWORD_ONLY and p["fuse_silu"].kind is inspect.Parameter.KEYWORD_ONLY
+    m = AWQW4A16Linear(256, 64, torch_dtype=torch.bfloat16)
+    assert m.qweight.shape == (16, 128) and m.qweight.dtype == torch.int32 and m.wscales.shape == (4, 64) and m.bias.shape == (64,)
+    x = torch.zeros(1, 4, 4, 16, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        dwconv_f16(x, torch.zeros(16, 3, 3, 1, dtype=torch.bfloat16))
+    assert list(inspect.signature(dwconv_f16).parameters) == ["input", "weight", "out", "bias"]          # src/kernels/dwconv.h:9
+    d = DWCONV(16, True, torch.float16)
+    assert d.weight.shape == (16, 3, 3, 1) and d.bias.shape == (16,)                                     # src/Linear.cpp:541-547
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        glue.layernorm_mod(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(64, dtype=torch.bfloat16), torch.zeros(64, dtype=torch.bfloat16))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            GraphedStep(lambda: None)
+    assert inspect.signature(svdq_gemm_w4a4_cuda).parameters["qkv_scratch"].kind is inspect.Parameter.KEYWORD_ONLY
