@@ -234,7 +234,7 @@ class StackRunner:
         n2 = n1 if b.tag.startswith("single") else glue.layernorm(o, None, None, 1e-6)
         fuse = self.fused._fuse_fc1(b.fc1, M)
         f = b.fc1.forward_mlp(n2, b.fc2, fuse=fuse)
-        self.launches += 1 + (1 + qkv_gemm_launches) + 2 + (0 if n2 is n1 else 1) + (3 if fuse else 4) + 1
+        self.launches += 1 + (1 + qkv_gemm_launches) + 2 + (0 if n2 is n1 else 1) + 4 + 1   # (fused MLP: quantize, fc1 + its partial-sum reduction, fc2; split: quantize, fc1, quantize, fc2)
         return glue.add(o, f)
 
     overlap_streams = True   # joint blocks: the 256-token text stream's kernels go to a second CUDA stream (they fill SMs the image stream's

@@ -175,11 +175,10 @@ typedef struct nb200_gemm_args {
     void *out_q, *out_k, *out_v;
     long long stride_head_q, stride_head_k, stride_head_v;
     int attn_tokens;
-    /* fused quantise epilogue with R_down > 0, optional: device scratch of >= nb200_gemm_workspace_bytes(Mp, R_down) bytes whose first
-     * 256-byte-rounded Mp/128 words are ZERO before the first use (the kernel leaves them zero).  With it the per-CTA partial projections of
-     * lora_act_out are reduced in a fixed order by the last CTA to arrive -- identical bits on every launch, no zero-fill of lora_act_out;
-     * without it (NULL / too small) they are added with fp32 atomics like the reference's red.global.add.f32 (lora.cuh:320-353), which is
-     * correct to fp32 rounding but not run-to-run bit-stable.  One workspace per concurrently running launch. */
+    /* fused quantise epilogue with R_down > 0, optional: device scratch of >= nb200_gemm_workspace_bytes(Mp, R_down) bytes.  With it the per-CTA
+     * partial projections of lora_act_out go to the scratch and a small second kernel adds them in a fixed order -- identical bits on every launch,
+     * no zero-fill of lora_act_out; without it (NULL / too small) they are added with fp32 atomics like the reference's red.global.add.f32
+     * (lora.cuh:320-353), which is correct to fp32 rounding but not run-to-run bit-stable.  One workspace per concurrently running launch. */
     void *workspace;
     long long workspace_bytes;
 } nb200_gemm_args;

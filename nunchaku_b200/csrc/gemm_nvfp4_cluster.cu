@@ -551,8 +551,10 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                 qkv_head = (col0 % third) >> 7;
                 do_rope = qkv_part < 2;
                 if (do_rope) {
-                    float sumsq = 0.f;
-                    auto acc_sq = [&](const uint32_t(&v)[32], const int cbase) {
+                    // sum of squares of the head's 128 columns: 8 partial sums of 16 columns (sequential FMA chains) combined by the fixed tree
+                    // ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)) -- the order csrc/rope.cu's 8-lanes-per-head reduction produces (bit-identical routes)
+                    auto sq32 = [&](const uint32_t(&v)[32], const int cbase) {   // -> p_even + p_odd of 32 columns
+                        float pa = 0.f, pb = 0.f;
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 cs = *reinterpret_cast<const float4 *>(cscale_s + cbase + i), bs = *reinterpret_cast<const float4 *>(bias_s + cbase + i);
@@ -560,16 +562,23 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                             const float y2 = fmaf(__uint_as_float(v[i + 2]), cs.z, bs.z), y3 = fmaf(__uint_as_float(v[i + 3]), cs.w, bs.w);
                             const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));   // fpsum is hT (epilogues.cuh:327-341)
                             const float2 r2 = Tr::to_float2(Tr::from_float2(make_float2(y2, y3)));
-                            sumsq = fmaf(r.x, r.x, sumsq);
-                            sumsq = fmaf(r.y, r.y, sumsq);
-                            sumsq = fmaf(r2.x, r2.x, sumsq);
-                            sumsq = fmaf(r2.y, r2.y, sumsq);
+                            if (i < 16) {
+                                pa = fmaf(r.x, r.x, pa);
+                                pa = fmaf(r.y, r.y, pa);
+                                pa = fmaf(r2.x, r2.x, pa);
+                                pa = fmaf(r2.y, r2.y, pa);
+                            } else {
+                                pb = fmaf(r.x, r.x, pb);
+                                pb = fmaf(r.y, r.y, pb);
+                                pb = fmaf(r2.x, r2.x, pb);
+                                pb = fmaf(r2.y, r2.y, pb);
+                            }
                         }
+                        return pa + pb;
                     };
-                    acc_sq(va, h * 128);
-                    acc_sq(vb, h * 128 + 32);
-                    acc_sq(vc, h * 128 + 64);
-                    acc_sq(vd, h * 128 + 96);
+                    const float q0 = sq32(va, h * 128) + sq32(vb, h * 128 + 32);
+                    const float q1 = sq32(vc, h * 128 + 64) + sq32(vd, h * 128 + 96);
+                    const float sumsq = q0 + q1;
                     rope_coef = rsqrt_approx_ftz(sumsq / 128.f + 1e-6f);
                     normw = s.normw + qkv_part * 128;
                     // reference pack_rotemb order (transformer_flux.py:60-92): float index of (row m, pair pr, sin|cos)

@@ -69,7 +69,6 @@ struct GemmParams {
     int R_down, Rdp;
     int tile_contig;         // 1: each CTA owns a contiguous range of tiles (same m-block runs), see EPI_QUANT
     float *ws_partial;       // EPI_QUANT, optional: [m-block + CTA][128 rows][Rdp] partial down projections (deterministic reduction) or null
-    unsigned int *ws_ticket; // [m-blocks], zero between launches (self-cleaning)
     // EPI_ROPE
     const void *norm_q, *norm_k;  // hT [128]
     const float *rotary;          // reference pack_rotemb layout [Mp][128]
@@ -86,7 +85,6 @@ struct GemmParams {
 enum { EPI_DEFAULT = 0, EPI_QUANT = 1, EPI_ROPE = 2 };
 constexpr int kMaxRdp = 128;  // largest fused next-layer rank (smem / TMEM budget)
 constexpr int kWsMaxCtas = 256;  // runs the deterministic-reduction workspace is sized for (one CTA per SM)
-inline long long kWsTicketBytes(int Mp) { return ((static_cast<long long>(Mp / 128) * 4 + 255) / 256) * 256; }
 
 template <bool FP4, int BN, int EPI = EPI_DEFAULT>
 struct Cfg {
@@ -164,7 +162,6 @@ struct alignas(1024) Smem {
     uint64_t stage_mma_done[2];
     uint64_t d2_full;
     uint32_t tmem_base;
-    uint32_t d2_is_last;
 };
 
 // cycle accounting of the barrier waits (written out only when p.prof != nullptr)
@@ -603,20 +600,34 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 qkv_head = nb % (p.num_n_blocks / 3);
                 do_rope = part < 2;
                 if (do_rope) {
-                    float sumsq = 0.f;
+                    // 8 partial sums of 16 columns (sequential FMA chains) combined by the fixed tree ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)): the
+                    // order of csrc/rope.cu's 8-lanes-per-head reduction and of the cluster kernel's epilogue (bit-identical routes)
+                    float sumsq = 0.f, pair = 0.f;
 #pragma unroll 1
                     for (int cc = 0; cc < 4 / H; cc++) {
                         const int c32 = h * (4 / H) + cc;
                         uint32_t v[32];
                         tmem_ld_32x32b_x32(taddr + c32 * 32, v);
                         tmem_ld_wait();
+                        float pa = 0.f, pb = 0.f;
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
                             const float y0 = fmaf(__uint_as_float(v[i]), s.cscale[c32 * 32 + i], s.bias[c32 * 32 + i]);
                             const float y1 = fmaf(__uint_as_float(v[i + 1]), s.cscale[c32 * 32 + i + 1], s.bias[c32 * 32 + i + 1]);
                             const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));  // fpsum is hT
-                            sumsq = fmaf(r.x, r.x, sumsq);
-                            sumsq = fmaf(r.y, r.y, sumsq);
+                            if (i < 16) {
+                                pa = fmaf(r.x, r.x, pa);
+                                pa = fmaf(r.y, r.y, pa);
+                            } else {
+                                pb = fmaf(r.x, r.x, pb);
+                                pb = fmaf(r.y, r.y, pb);
+                            }
+                        }
+                        if ((cc & 1) == 0) {
+                            pair = pa + pb;
+                        } else {
+                            const float quad = pair + (pa + pb);
+                            sumsq = cc == 1 ? quad : sumsq + quad;
                         }
                     }
                     if constexpr (H == 2) {  // each group saw 64 of the head's 128 columns
@@ -894,8 +905,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         if (p.ws_partial != nullptr) {
                             // Deterministic reduction (the reference adds its partials with red.global.add.f32, launch_impl:252 +
                             // lora.cuh:320-353): this CTA's run of the m-block goes to workspace slot mb + blockIdx.x (runs ordered by (m-block, CTA)
-                            // form a staircase, so the sum is unique per run); the LAST run to arrive (ticket) adds all of the m-block's runs in
-                            // CTA order and stores the result -- lora_act_out needs no zero-fill and every launch gives the same bits.
+                            // form a staircase, so the index is unique per run); lora_partials_reduce_kernel, launched behind this grid, adds an
+                            // m-block's runs in CTA order -- lora_act_out needs no zero-fill and every launch gives the same bits.
                             float *mine = p.ws_partial + (static_cast<size_t>(mb + blockIdx.x) * BM + row) * p.Rdp;
                             for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
                                 uint32_t d2[16];
@@ -907,41 +918,6 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                                                                                                         __uint_as_float(d2[i + 2]), __uint_as_float(d2[i + 3])));
                             }
                             tc_fence_before_sync();
-                            __threadfence();
-                            named_bar_sync(1, C::kEpiThreads);
-                            // CTAs whose tile range touches this m-block: owner(t) = ceil((t + 1) * grid / tiles) - 1
-                            const long long t_first = static_cast<long long>(mb) * p.num_n_blocks, t_last = t_first + p.num_n_blocks - 1;
-                            const int b_first = static_cast<int>(((t_first + 1) * gridDim.x + p.num_tiles - 1) / p.num_tiles) - 1;
-                            const int b_last = static_cast<int>(((t_last + 1) * gridDim.x + p.num_tiles - 1) / p.num_tiles) - 1;
-                            if (eta == 0) {
-                                const unsigned int ticket = atomicAdd(&p.ws_ticket[mb], 1u);
-                                const bool last = ticket == static_cast<unsigned int>(b_last - b_first);
-                                if (last) p.ws_ticket[mb] = 0;   // self-cleaning for the next launch
-                                s.d2_is_last = last ? 1u : 0u;
-                            }
-                            named_bar_sync(1, C::kEpiThreads);
-                            if (s.d2_is_last) {
-                                __threadfence();
-                                for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
-                                    float acc16[16];
-#pragma unroll
-                                    for (int i = 0; i < 16; i++) acc16[i] = 0.f;
-                                    for (int b = b_first; b <= b_last; b++) {
-                                        const float *src = p.ws_partial + (static_cast<size_t>(mb + b) * BM + row) * p.Rdp + c16 * 16;
-#pragma unroll
-                                        for (int i = 0; i < 16; i += 4) {
-                                            const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + i));
-                                            acc16[i] += v.x;
-                                            acc16[i + 1] += v.y;
-                                            acc16[i + 2] += v.z;
-                                            acc16[i + 3] += v.w;
-                                        }
-                                    }
-#pragma unroll
-                                    for (int i = 0; i < 16; i++)
-                                        if (c16 * 16 + i < p.R_down) dst[c16 * 16 + i] = acc16[i];
-                                }
-                            }
                         } else {
                             // two groups: each adds half of the 16-rank column blocks
                             for (int c16 = h; c16 * 16 < p.Rdp; c16 += H) {
@@ -1030,6 +1006,34 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// lora_act_out[m-block rows][R] = sum over the CTAs whose tile range touched the m-block, in CTA order, of the partial projections the fused
+// quantise epilogue left in the workspace (slot = m-block + CTA).  grid (m-blocks, 128 / kReduceRows), one thread per (row, 4 ranks).
+constexpr int kReduceRows = 16;
+__global__ void __launch_bounds__(kReduceRows * 8) lora_partials_reduce_kernel(const float *__restrict__ ws, float *__restrict__ out, int R, int num_n_blocks,
+                                                                                int num_tiles, int gemm_grid) {
+    ptx::griddep_launch_dependents();
+    ptx::griddep_wait();   // the partials are the GEMM's output
+    const int mb = blockIdx.x;
+    // CTA b of the GEMM owns tiles [tiles * b / grid, tiles * (b + 1) / grid): owner(t) = ceil((t + 1) * grid / tiles) - 1
+    const long long t_first = static_cast<long long>(mb) * num_n_blocks, t_last = t_first + num_n_blocks - 1;
+    const int b_first = static_cast<int>(((t_first + 1) * gemm_grid + num_tiles - 1) / num_tiles) - 1;
+    const int b_last = static_cast<int>(((t_last + 1) * gemm_grid + num_tiles - 1) / num_tiles) - 1;
+    const int r4 = R / 4;
+    for (int idx = threadIdx.x; idx < kReduceRows * r4; idx += blockDim.x) {
+        const int row = blockIdx.y * kReduceRows + idx / r4, c4 = idx % r4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int b = b_first; b <= b_last; b++) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(ws + (static_cast<size_t>(mb + b) * 128 + row) * R) + c4);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+        }
+        *(reinterpret_cast<float4 *>(out + (static_cast<size_t>(mb) * 128 + row) * R) + c4) = acc;
+    }
+}
+
 template <bool FP4, typename hT, int BN, int EPI>
 int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     using C = Cfg<FP4, BN, EPI>;
@@ -1096,11 +1100,8 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.R_down = a.R_down;
     p.Rdp = rdp;
     p.ws_partial = nullptr;
-    p.ws_ticket = nullptr;
-    if (EPI == EPI_QUANT && a.R_down > 0 && a.workspace != nullptr && a.workspace_bytes >= nb200_gemm_workspace_bytes(a.Mp, a.R_down)) {
-        p.ws_ticket = static_cast<unsigned int *>(a.workspace);
-        p.ws_partial = reinterpret_cast<float *>(static_cast<uint8_t *>(a.workspace) + kWsTicketBytes(a.Mp));
-    }
+    if (EPI == EPI_QUANT && a.R_down > 0 && a.workspace != nullptr && a.workspace_bytes >= nb200_gemm_workspace_bytes(a.Mp, a.R_down))
+        p.ws_partial = static_cast<float *>(a.workspace);
     p.norm_q = a.norm_q;
     p.norm_k = a.norm_k;
     p.rotary = a.rotary_emb;
@@ -1127,6 +1128,12 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     NB200_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, kern, tm_act, tm_wgt, tm_out, tm_ld, p));
     count_launch();
     NB200_CUDA_CHECK(cudaGetLastError());
+    if (p.ws_partial != nullptr) {   // the fixed-order sum of the per-CTA partial projections
+        LaunchCfg lr(dim3(a.Mp / BM, BM / kReduceRows), dim3(kReduceRows * 8), 0, stream);
+        NB200_CUDA_CHECK(cudaLaunchKernelEx(&lr.cfg, lora_partials_reduce_kernel, static_cast<const float *>(p.ws_partial), a.lora_act_out, a.R_down, p.num_n_blocks,
+                                            p.num_tiles, grid));
+        count_launch();
+    }
     return NB200_OK;
 }
 
@@ -1169,11 +1176,10 @@ int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
 }  // namespace
 }  // namespace nb200
 
-// ticket area (one u32 per 128-row block, rounded to 256 B, ZERO before the first use, self-cleaning afterwards) + one [128][R_down] fp32 slot
-// per (m-block, CTA) run
+// one [128][R_down] fp32 slot per (m-block, CTA) run
 extern "C" __attribute__((visibility("default"))) long long nb200_gemm_workspace_bytes(int Mp, int R_down) {
     if (Mp <= 0 || R_down <= 0) return 0;
-    return nb200::kWsTicketBytes(Mp) + (static_cast<long long>(Mp / 128) + nb200::kWsMaxCtas) * 128 * R_down * 4;
+    return (static_cast<long long>(Mp / 128) + nb200::kWsMaxCtas) * 128 * R_down * 4;
 }
 
 extern "C" __attribute__((visibility("default"))) int nb200_gemm_w4a4(const nb200_gemm_args *a, void *stream_) {

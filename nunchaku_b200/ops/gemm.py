@@ -305,11 +305,11 @@ _ws_cache: dict[tuple, torch.Tensor] = {}
 
 def _reduce_workspace(Mp: int, rank: int, device) -> torch.Tensor:
     """Scratch of the fused quantise epilogue's deterministic reduction (include/nunchaku_b200.h: nb200_gemm_args.workspace), one per
-    (device, stream, size): zero-initialised once, the kernel keeps its ticket words zero."""
+    (device, stream, size)."""
     key = (str(device), torch.cuda.current_stream(device).cuda_stream, Mp, rank)
     ws = _ws_cache.get(key)
     if ws is None:
-        ws = torch.zeros(int(lib.nb200_gemm_workspace_bytes(Mp, rank)), dtype=torch.uint8, device=device)
+        ws = torch.empty(int(lib.nb200_gemm_workspace_bytes(Mp, rank)), dtype=torch.uint8, device=device)
         _ws_cache[key] = ws
     return ws
 
