@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define NB200_ABI_VERSION 1
+#define NB200_ABI_VERSION 2
 
 typedef enum nb200_status {
     NB200_OK = 0,
@@ -181,6 +181,13 @@ typedef struct nb200_gemm_args {
      * (lora.cuh:320-353), which is correct to fp32 rounding but not run-to-run bit-stable.  One workspace per concurrently running launch. */
     void *workspace;
     long long workspace_bytes;
+    /* SANA linear attention as a GEMM epilogue (EpilogueLiteLA, src/kernels/zgemm/epilogues.cuh:552-691; wiring gemm_w4a4_launch_impl.cuh:311-346),
+     * optional: out_vk f32 [Mp / vk_tokens, N / 96, 33, 32] (zero-filled inside the call, accumulated with fp32 atomics like the reference's
+     * reduce_add) and `out` = relu(Q) hT [Mp, N / 3] (M_out = Mp, N_out = N / 3).  Channel layout of the projection: [ Q (N/3) | per head: K (32),
+     * V (32) ]; vk[v][k] = sum_t V[t,v] relu(K[t,k]), vk[32][k] = sum_t relu(K[t,k]) over the vk_tokens rows of an image.  Needs (N / 3) % 128 == 0
+     * (the reference asserts numBlocksN % 3 == 0) and vk_tokens % 128 == 0; other shapes: plain GEMM + nb200_litela_vk below.                      */
+    float *out_vk;
+    int vk_tokens;
 } nb200_gemm_args;
 
 int nb200_gemm_w4a4(const nb200_gemm_args *args, void *stream);

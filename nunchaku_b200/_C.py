@@ -83,6 +83,8 @@ class GemmArgs(ctypes.Structure):
         ("attn_tokens", c_int),
         ("workspace", c_void_p),
         ("workspace_bytes", c_longlong),
+        ("out_vk", c_void_p),
+        ("vk_tokens", c_int),
     ]
 
 
@@ -144,4 +146,4 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (status {status}): {msg.decode() if msg else '?'}")
 
 
-assert lib.nb200_abi_version() == 1, "nunchaku_b200: stale shared library (ABI version mismatch); rebuild"
+assert lib.nb200_abi_version() == 2, "nunchaku_b200: stale shared library (ABI version mismatch); rebuild"

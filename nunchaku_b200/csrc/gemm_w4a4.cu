@@ -75,6 +75,9 @@ struct GemmParams {
     __half *out_qkv[3];           // EpiloguePackQKV: fp16 [heads][rows][128] each (null: store `out`)
     long long stride_head[3];
     int attn_tokens;
+    // EPI_LITELA (SANA linear attention, epilogues.cuh:552-691): `out` is relu(Q) [Mp, N/3]; the K | V tiles are reduced over tokens into out_vk
+    float *out_vk;                // f32 [batch][heads][33][32], zero before the launch, accumulated with fp32 atomics (as the reference's reduce_add)
+    int vk_tokens, vk_heads;      // tokens per batch (multiple of 128: a tile never straddles two images), heads = N / 96
     long long *prof;              // optional [grid][16] cycle counters (tools/gemm_prof.py)
     int debug;                    // NB200_GEMM_DEBUG experiment bits (results invalid when non-zero): 1 = converters
                                   // skip their smem stores, 2 = converters skip all work, 4 = no main-loop MMAs, 8 = epilogue drains TMEM but skips math/stores,
@@ -82,7 +85,7 @@ struct GemmParams {
     float lora_scales[NB200_MAX_LORA_SCALES];
 };
 
-enum { EPI_DEFAULT = 0, EPI_QUANT = 1, EPI_ROPE = 2 };
+enum { EPI_DEFAULT = 0, EPI_QUANT = 1, EPI_ROPE = 2, EPI_LITELA = 3 };
 constexpr int kMaxRdp = 128;  // largest fused next-layer rank (smem / TMEM budget)
 constexpr int kWsMaxCtas = 256;  // runs the deterministic-reduction workspace is sized for (one CTA per SM)
 
@@ -122,6 +125,9 @@ struct Cfg {
     static_assert(kNumAcc * BN <= 512, "TMEM budget");
     static_assert(EPI != EPI_QUANT || ((BN == 128 || !FP4) && kTmemLd + kMaxRdp <= 512), "fused quantise epilogue: TMEM budget");
     static_assert(EPI != EPI_ROPE || BN == 128, "RMSNorm+RoPE epilogue: one 128-wide head per tile");
+    // EPI_LITELA: a 128-wide K | V tile = two heads of [K 32 | V 32]; its [128 x 128] fp32 Gram accumulator sits behind the main accumulators
+    static constexpr int kTmemVk = kTmemLd;
+    static_assert(EPI != EPI_LITELA || (BN == 128 && kNumAcc == 2 && kTmemVk + 128 <= 512), "LiteLA epilogue: tile shape / TMEM budget");
 };
 
 template <bool FP4, int BN, int EPI = EPI_DEFAULT>
@@ -161,6 +167,7 @@ struct alignas(1024) Smem {
     uint64_t ld_b_empty;
     uint64_t stage_mma_done[2];
     uint64_t d2_full;
+    uint64_t vk_full;
     uint32_t tmem_base;
 };
 
@@ -273,6 +280,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         mbar_init(&s.stage_mma_done[0], 1);
         mbar_init(&s.stage_mma_done[1], 1);
         mbar_init(&s.d2_full, C::kEpiGroups);
+        mbar_init(&s.vk_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(&s.tmem_base);
@@ -475,7 +483,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
         uint32_t store_count = 0;
         long long t_tmem_full = 0, t_pre = 0;
         const long long t_epi0 = clock64();
-        [[maybe_unused]] uint32_t ld_phase = 0, d2_phase = 0;
+        [[maybe_unused]] uint32_t ld_phase = 0, d2_phase = 0, vk_phase = 0;
         [[maybe_unused]] uint32_t smd_phase[2] = {0, 0};
         if constexpr (EPI == EPI_ROPE) {
             for (int i = eta; i < 256; i += C::kEpiThreads)
@@ -594,6 +602,8 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
             [[maybe_unused]] float rope_coef = 1.f;
             [[maybe_unused]] const float *normw = s.aux;
             [[maybe_unused]] const float *rot_row = nullptr;
+            [[maybe_unused]] bool vk_tile = false;   // EPI_LITELA: a K | V tile (reduced into out_vk, nothing stored) vs a Q tile (relu, stored)
+            if constexpr (EPI == EPI_LITELA) vk_tile = nb >= p.num_n_blocks / 3;
             if constexpr (EPI == EPI_ROPE) {
                 const int part = nb / (p.num_n_blocks / 3);  // 0 = Q heads, 1 = K heads, 2 = V (untouched)
                 qkv_part = part;
@@ -657,10 +667,14 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                 [[maybe_unused]] bool pack_qkv = false;
                 if constexpr (EPI == EPI_ROPE) pack_qkv = p.out_qkv[0] != nullptr;
                 if (et == 0 && !pack_qkv) {
-                    if constexpr (H == 2)
+                    if constexpr (H == 2) {
                         bulk_wait_group_read<0>();
-                    else
-                        bulk_wait_group_read<1>();
+                    } else {
+                        if (vk_tile)   // (a K | V tile commits no store group: "all but the newest" would not cover the other buffer's store)
+                            bulk_wait_group_read<0>();
+                        else
+                            bulk_wait_group_read<1>();
+                    }
                 }
                 if constexpr (EPI == EPI_QUANT) {
                     if (p.R_down > 0) mbar_wait(&s.stage_mma_done[buf], smd_phase[buf] ^ 1);
@@ -702,6 +716,14 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                                 const float2 sc = *reinterpret_cast<const float2 *>(rot_row + (pr >> 2) * 128 + (pr & 3) * 4);
                                 y0 = x0 * sc.y - x1 * sc.x;  // (sin, cos) = (sc.x, sc.y)  epilogues.cuh:362-367
                                 y1 = x0 * sc.x + x1 * sc.y;
+                            }
+                        } else if constexpr (EPI == EPI_LITELA) {
+                            // relu on the hT value: every column of a Q tile (epilogues.cuh:676-688), the K half (first 32 columns) of each
+                            // head of a K | V tile (epilogues.cuh:611-613)
+                            if (!vk_tile || col < 32) {
+                                const float2 r = Tr::to_float2(Tr::from_float2(make_float2(y0, y1)));
+                                y0 = fmaxf(r.x, 0.f);
+                                y1 = fmaxf(r.y, 0.f);
                             }
                         } else {
                             if (p.mid_act != NB200_ACT_NONE) {
@@ -752,7 +774,7 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                     if (p.R_down > 0 && h == 1 && q == 0) asm volatile("bar.sync 6, 64;" ::: "memory");
                 }
                 if (et == 0) {
-                    if (EPI != EPI_QUANT || p.out != nullptr) {
+                    if ((EPI != EPI_QUANT || p.out != nullptr) && !vk_tile) {
                         tma_store_2d(&tm_out, s.out_stage[buf], n0 + ch * 64, m0);
                         bulk_commit_group();
                     }
@@ -889,6 +911,60 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
                         mbar_arrive(&s.tmem_empty[acc]);
                     }
                     if (!(p.debug & 8)) do_chunk(ch, v0, v1);
+                }
+            }
+            if constexpr (EPI == EPI_LITELA) {
+                if (vk_tile) {
+                    // EpilogueLiteLA (epilogues.cuh:571-660): the tile's two heads, [K 32 | V 32] each, are staged as hT [128 tokens][64] per head in the
+                    // two store buffers (relu already on K).  The token reduction  vk[v][k] = sum_t V[t,v] relu(K[t,k])  is a GEMM with the TOKENS as
+                    // its K dimension: both operands are the staged tile read as an MN-major SW128 operand (the layout csrc/attention.cu feeds V
+                    // with), D[128 x 128] = X^T X in fp32 -- the reference's mma_f16xf16_f32 on transposed fragments.  Head hd's state is the
+                    // block D[64 hd + 32 .. 64 hd + 63][64 hd .. 64 hd + 31] = TMEM lanes of the warps q = 1 / q = 3, 32 columns each; the
+                    // other blocks (K^T K, V^T V, cross-head) are computed and ignored: 8 instructions of 64 clk per tile.
+                    named_bar_sync(1, C::kEpiThreads);   // both heads staged (every thread fenced its writes for the async proxy before its group barrier)
+                    if (eta == 0) {
+                        tc_fence_after_sync();
+                        const uint32_t x_addr = smem_u32(s.out_stage[0]);
+                        constexpr uint32_t idesc_vk = make_idesc_f16(Tr::kIsBf16, 128, 128) | (1u << 15) | (1u << 16);   // A and B MN-major
+#pragma unroll
+                        for (int ks = 0; ks < BM / 16; ks++) {   // 16 tokens per instruction: 2 groups of 8 rows = 2 KB further
+                            const uint64_t xd = make_smem_desc(x_addr + ks * 2048, BM * 128, 1024, kLayoutSw128);   // LBO = distance between the two heads' buffers
+                            tc_mma_f16(tmem_base + C::kTmemVk, xd, xd, idesc_vk, ks != 0);
+                        }
+                        tc_commit(&s.vk_full);
+                    }
+                    const int batch = m0 / p.vk_tokens;
+                    float *vk_tile_out = p.out_vk + (static_cast<size_t>(batch) * p.vk_heads + (nb - p.num_n_blocks / 3) * 2) * (33 * 32);
+                    // row 32 of the state, sum_t relu(K[t, k]) (the reference multiplies by a fragment of ones, epilogues.cuh:626-655): column sums
+                    // of the staged K halves on the CUDA cores while the tensor core works -- thread = (column j, quarter of the rows)
+                    {
+                        const int j = et & 31, part = et >> 5;
+#pragma unroll 1
+                        for (int cc = 0; cc < CH / H; cc++) {
+                            const int hd = h * (CH / H) + cc;
+                            const uint8_t *xt = s.out_stage[hd];
+                            float sum = 0.f;
+#pragma unroll 8
+                            for (int r = 0; r < 32; r++) {
+                                const int t = part * 32 + r;
+                                sum += Tr::to_float(*reinterpret_cast<const hT *>(xt + t * 128 + (((j >> 3) ^ (t & 7)) << 4) + (j & 7) * 2));
+                            }
+                            atomicAdd(vk_tile_out + hd * (33 * 32) + 32 * 32 + j, sum);
+                        }
+                    }
+                    mbar_wait(&s.vk_full, vk_phase);
+                    vk_phase ^= 1;
+                    tc_fence_after_sync();
+                    if (h == 0 && (q & 1)) {
+                        const int hd = q >> 1;
+                        uint32_t d[32];
+                        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kTmemVk + hd * 64, d);
+                        tmem_ld_wait();
+                        float *dst = vk_tile_out + hd * (33 * 32) + lane * 32;   // this thread's V index = lane
+#pragma unroll
+                        for (int i = 0; i < 32; i++) atomicAdd(dst + i, __uint_as_float(d[i]));
+                    }
+                    tc_fence_before_sync();   // (the next tile's barrier orders these TMEM / shared-memory reads before the buffers are written again)
                 }
             }
             if constexpr (EPI == EPI_QUANT) {
@@ -1112,6 +1188,11 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     p.stride_head[1] = a.stride_head_k;
     p.stride_head[2] = a.stride_head_v;
     p.attn_tokens = a.attn_tokens;
+    p.out_vk = a.out_vk;
+    p.vk_tokens = a.vk_tokens;
+    p.vk_heads = a.N / 96;
+    if (EPI == EPI_LITELA)   // the reference zero-fills out_vk inside the op as well (launch_impl:336)
+        NB200_CUDA_CHECK(cudaMemsetAsync(a.out_vk, 0, static_cast<size_t>(a.Mp / a.vk_tokens) * p.vk_heads * 33 * 32 * sizeof(float), stream));
     for (int i = 0; i < NB200_MAX_LORA_SCALES; i++) p.lora_scales[i] = a.lora_scales[i];
 
     int num_sms_dev = 0;
@@ -1139,6 +1220,7 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
 
 template <bool FP4, typename hT>
 int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
+    if (a.out_vk != nullptr) return launch<FP4, hT, 128, EPI_LITELA>(a, stream);   // SANA linear attention: two heads of [K 32 | V 32] per 128-wide tile
     if (a.qout != nullptr) {
         // INT4: 256-wide tiles halve the converter work per MMA cycle (the INT4 limiter); needs the next layer's rank to fit
         // the smaller smem / TMEM budget.  block_n = 128 forces the narrow tile.  (NVFP4: the 256-wide variant does not fit smem.)
@@ -1223,9 +1305,17 @@ extern "C" __attribute__((visibility("default"))) int nb200_gemm_w4a4(const nb20
                           a->stride_head_q % 8 == 0 && a->stride_head_k % 8 == 0 && a->stride_head_v % 8 == 0,
                       "out_q/k/v must be 16-byte aligned");
     }
+    if (a->out_vk != nullptr) {
+        // EpilogueLiteLA (launch_impl:311-346): out = relu(Q) [Mp, N/3], out_vk [Mp / vk_tokens][N / 96][33][32] f32
+        NB200_REQUIRE(a->out != nullptr && a->qout == nullptr && a->rotary_emb == nullptr && a->mid_act == NB200_ACT_NONE,
+                      "out_vk goes with out (= out_linearattn) only");
+        NB200_REQUIRE(a->N % 384 == 0, "LiteLA epilogue: N / 3 must be a multiple of 128 (numBlocksN % 3 == 0, epilogues.cuh:585)");
+        NB200_REQUIRE(a->vk_tokens > 0 && a->vk_tokens % 128 == 0 && a->Mp % a->vk_tokens == 0, "vk_tokens must be a multiple of 128 that divides Mp");
+        NB200_REQUIRE(a->M_out == a->Mp && a->N_out == a->N / 3, "LiteLA epilogue: out is [Mp, N / 3]");
+    }
     if (a->out != nullptr) {
         NB200_REQUIRE(a->M_out > 0 && a->M_out <= a->Mp && a->Mp - a->M_out < 256, "M_out must be in (Mp-256, Mp]");
-        NB200_REQUIRE(a->N_out > 0 && a->N_out <= a->N && a->N - a->N_out < 128, "N_out must be in (N-128, N]");
+        NB200_REQUIRE(a->out_vk != nullptr || (a->N_out > 0 && a->N_out <= a->N && a->N - a->N_out < 128), "N_out must be in (N-128, N]");
         NB200_REQUIRE(a->N_out % 8 == 0, "out row pitch must be a multiple of 16 bytes (TMA store)");
         NB200_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "out must be 16-byte aligned");
     }

@@ -3,9 +3,10 @@
 //   vk_mul_q_kernel           src/kernels/zgemm/epilogues.cuh:693-760 (launcher gemm_w4a4_launch_impl.cuh:427-448)
 //
 // The reference computes relu(Q) and the per-head [33 x 32] state  vk[v][k] = sum_t V[t,v] * relu(K[t,k])
-// (row 32: sum_t relu(K[t,k])) inside the GEMM epilogue.  Here the GEMM writes the plain hT tile and
-// `litela_vk_kernel` consumes it while it is still L2-resident (SANA: [B*1024, 6720] bf16 = 13 MB against a
-// 126 MB L2), which keeps the fused-GEMM epilogue set small; same arithmetic: relu and the operands in hT,
+// (row 32: sum_t relu(K[t,k])) inside the GEMM epilogue, and so does gemm_w4a4.cu's EPI_LITELA (NVFP4, N / 3 a multiple of 128: DESIGN.md
+// section 4.3).  This file is the other route -- INT4 (measured faster split) and odd shapes: the GEMM writes the plain hT tile and
+// `litela_vk_kernel` consumes it while it is still L2-resident (SANA: [B*1024, 6912] bf16 = 28 MB against a
+// 126 MB L2); same arithmetic: relu and the operands in hT,
 // products and sums in fp32, partial sums of token blocks combined with fp32 atomics (reference: reduce_add
 // per 256-token block).  Channel layout of the projection output (N = 3 * heads * 32): [ Q (N/3) | per head:
 // K (32), V (32) ].

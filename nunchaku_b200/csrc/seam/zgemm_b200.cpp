@@ -263,9 +263,17 @@ void gemm_w4a4(Tensor act, Tensor wgt, Tensor out, Tensor qout, Tensor ascales, 
     a.act_unsigned = act_unsigned;
     a.mid_act = fuse_silu ? NB200_ACT_SILU : NB200_ACT_NONE;
 
-    Tensor scratch;  // SANA LiteLA: plain projection into an L2-resident scratch, reduced by nb200_litela_vk
+    // SANA LiteLA (launch_impl:311-346).  NVFP4 at the reference's shapes (N / 3 a multiple of 128): the reduction runs inside the GEMM epilogue
+    // (csrc/gemm_w4a4.cu EPI_LITELA, measured 42 vs 73 us at SANA-1.6B's QKV projection); otherwise (INT4: measured 146 vs 155 us) the plain
+    // projection goes to an L2-resident scratch that nb200_litela_vk reduces.
+    Tensor scratch;
     const bool litela = out_vk.valid();
-    if (litela) {
+    const bool litela_fused = litela && fp4 && (a.N / 3) % 128 == 0 && out_linearattn.shape[1] % 128 == 0;
+    if (litela_fused) {
+        out = out_linearattn;
+        a.out_vk = out_vk.data_ptr<float>();
+        a.vk_tokens = out_linearattn.shape[1];
+    } else if (litela) {
         scratch = Tensor::allocate({a.Mp, a.N}, st, act.device());
         out = scratch;
     }
@@ -297,7 +305,7 @@ void gemm_w4a4(Tensor act, Tensor wgt, Tensor out, Tensor qout, Tensor ascales, 
         a.rotary_emb = rotary_emb.data_ptr<float>();
     }
     check(nb200_gemm_w4a4(&a, stream()), "nb200_gemm_w4a4");
-    if (litela) {
+    if (litela && !litela_fused) {
         const int batch = out_linearattn.shape[0], tokens = out_linearattn.shape[1];
         check(nb200_litela_vk(a.dtype, scratch.data_ptr(), out_linearattn.data_ptr(), out_vk.data_ptr<float>(), batch, tokens, a.N, stream()),
               "nb200_litela_vk");

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -24,6 +25,10 @@ from ..utils import on_device_of, torch_dtype_code
 BLOCK_N_OVERRIDE = 0
 NUM_SMS_OVERRIDE = 0
 PROF_BUFFER = None   # torch int64 tensor [grid, 16]: per-CTA barrier-wait cycle counters (tools/gemm_prof.py)
+# SANA linear attention: True = EpilogueLiteLA inside the GEMM (csrc/gemm_w4a4.cu, EPI_LITELA); False = plain GEMM + nb200_litela_vk; None = by
+# measurement (tools/litela_bench.py, profiles/r02i_litela_bench.json, SANA-1.6B's 2 x 1024 x 2304 -> 6912 projection): NVFP4 fused (42 vs 73 us),
+# INT4 split (146 vs 155 us: one epilogue warpgroup next to 24 converter warps)
+LITELA_FUSED = {"fused": True, "split": False}.get(os.environ.get("NB200_LITELA", "auto"))
 
 
 @dataclass
@@ -55,6 +60,8 @@ class _Call:
     rotary_emb: torch.Tensor | None = None
     out_qkv: tuple | None = None
     attn_tokens: int = 0
+    out_vk: torch.Tensor | None = None      # LiteLA epilogue: `out` is relu(Q) [Mp, N/3]
+    vk_tokens: int = 0
     act_unsigned: bool = False
     mid_act: int = NB200_ACT_NONE
     extra: dict = field(default_factory=dict)
@@ -124,6 +131,8 @@ def _launch(c: _Call) -> None:
             args.out_q, args.out_k, args.out_v = oq.data_ptr(), ok_.data_ptr(), ov.data_ptr()
             args.stride_head_q, args.stride_head_k, args.stride_head_v = oq.stride(1), ok_.stride(1), ov.stride(1)
             args.attn_tokens = int(c.attn_tokens)
+    if c.out_vk is not None:
+        args.out_vk, args.vk_tokens = c.out_vk.data_ptr(), int(c.vk_tokens)
     args.dtype = torch_dtype_code(c.dtype)
     args.fp4 = int(c.fp4)
     args.act_unsigned = int(c.act_unsigned)
@@ -211,16 +220,23 @@ def svdq_gemm_w4a4_cuda(
     if not act.is_cuda:
         raise RuntimeError("nunchaku_b200 has no CPU path: act must be a CUDA tensor")
     litela = out_vk is not None or out_linearattn is not None
+    litela_fused = False
     if litela:
         # SANA linear attention (launch_impl:311-346): relu(Q) -> out_linearattn, per-head V^T relu(K) state -> out_vk.
-        # The GEMM writes the plain hT projection into a scratch tensor and nb200_litela_vk reduces it while it is L2-hot.
+        # Fused route (LITELA_FUSED, the reference's shapes: N / 3 a multiple of 128): the GEMM's own epilogue reduces the K | V tiles on the
+        # tensor cores (csrc/gemm_w4a4.cu, EPI_LITELA) and stores relu(Q).  Other shapes: the GEMM writes the plain hT projection into a scratch
+        # tensor and nb200_litela_vk reduces it while it is L2-hot.
         _require(out_vk is not None and out_linearattn is not None, "out_vk and out_linearattn go together (launch_impl:313)")
         _require(out_vk.dtype == torch.float32 and out_vk.dim() == 4 and tuple(out_vk.shape[2:]) == (33, 32), "out_vk must be float32 [B, heads, 33, 32]")
         _require(out_linearattn.dim() == 3 and out_linearattn.shape[0] == out_vk.shape[0], "out_linearattn must be [B, tokens, N / 3]")
         _require(out_vk.is_contiguous() and out_linearattn.is_contiguous(), "out_vk / out_linearattn must be contiguous")
         _require(out_linearattn.shape[1] % 256 == 0, "tokens must be a multiple of 256 (launch_impl:331)")
         _require(out_vk.shape[1] * 96 == wgt.shape[0] and out_linearattn.shape[2] * 3 == wgt.shape[0], "N must be 3 * heads * 32")
-        out = torch.empty(out_linearattn.shape[0] * out_linearattn.shape[1], wgt.shape[0], dtype=out_linearattn.dtype, device=act.device)
+        litela_fused = (fp4 if LITELA_FUSED is None else LITELA_FUSED) and (wgt.shape[0] // 3) % 128 == 0
+        if litela_fused:
+            out = out_linearattn.view(-1, out_linearattn.shape[2])
+        else:
+            out = torch.empty(out_linearattn.shape[0] * out_linearattn.shape[1], wgt.shape[0], dtype=out_linearattn.dtype, device=act.device)
     pack_qkv = out_q is not None or out_k is not None or out_v is not None
     if pack_qkv:
         # EpiloguePackQKV (launch_impl:376-393): fp16 [B=1, heads, rows >= Mp, 128], plain row-major inside a head
@@ -272,13 +288,16 @@ def svdq_gemm_w4a4_cuda(
               lora_up=repack.lora_up(lora_up, cs) if rank > 0 else None, rank=rank, lora_scales=lora_scales, out=out, act_unsigned=act_unsigned,
               mid_act=_mid_act(fuse_silu, fuse_gelu), norm_q=norm_q, norm_k=norm_k, rotary_emb=rotary_emb,
               out_qkv=(out_q, out_k, out_v) if pack_qkv else None, attn_tokens=attn_tokens)
+    if litela_fused:
+        _require(out.shape[0] == act.numel() // act.shape[-1], "out_linearattn: batch * tokens must equal the padded row count of act")
+        c.out_vk, c.vk_tokens = out_vk, out_linearattn.shape[1]
     if fused_quant:
         c.qout, c.oscales = qout, oscales
         c.smooth_next = repack.channel_vector(smooth_factor, out_f32=False)
         if lora_down is not None and lora_down.shape[1] > 0:
             c.lora_down_next, c.lora_act_out, c.rank_down = repack.lora_down_next(lora_down), lora_act_out, lora_down.shape[1]
     _launch(c)
-    if litela:
+    if litela and not litela_fused:
         Mp = act.numel() // act.shape[-1]
         _require(out.shape[0] == Mp, "out_linearattn: batch * tokens must equal the padded row count of act")
         check(lib.nb200_litela_vk(torch_dtype_code(out.dtype), out.data_ptr(), out_linearattn.data_ptr(), out_vk.data_ptr(),

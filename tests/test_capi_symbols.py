@@ -32,7 +32,7 @@ def test_abi_version_and_argument_validation_without_gpu():
 
     from nunchaku_b200._C import GemmArgs, QuantizeArgs
 
-    assert lib.nb200_abi_version() == 1
+    assert lib.nb200_abi_version() == 2
     # NULL / malformed arguments are rejected on the host before any CUDA call
     assert lib.nb200_quantize_w4a4_act_fuse_lora(None, None) == -1
     assert b"NULL" in lib.nb200_last_error()
@@ -52,7 +52,7 @@ def test_struct_layout_matches_header_sizes():
     from nunchaku_b200._C import GemmArgs, QuantizeArgs
 
     assert ctypes.sizeof(QuantizeArgs) == 104
-    assert ctypes.sizeof(GemmArgs) == 528
+    assert ctypes.sizeof(GemmArgs) == 544
 
 
 def test_struct_layout_matches_a_c_compiler(tmp_path):
