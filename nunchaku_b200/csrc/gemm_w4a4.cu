@@ -1082,11 +1082,14 @@ gemm_w4a4_kernel(const __grid_constant__ CUtensorMap tm_act, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// lora_act_out[m-block rows][R] = sum over the CTAs whose tile range touched the m-block, in CTA order, of the partial projections the fused
-// quantise epilogue left in the workspace (slot = m-block + CTA).  grid (m-blocks, 128 / kReduceRows), one thread per (row, 4 ranks).
+// lora_act_out[m-block rows][R] = sum over the CTAs whose tile range touched the m-block of the partial projections the fused quantise epilogue left
+// in the workspace (slot = m-block + CTA), in a FIXED order: four lanes share one (row, 4 ranks) output, lane p adds the p-th quarter of the runs
+// in CTA order and the quarters are combined as (q0 + q1) + (q2 + q3) -- identical bits on every launch, a serial chain of ~19 adds instead of ~74
+// at FLUX's text-stream shape (r02h launch list: 28.9 us cold for 2.4 MB of partials with one thread per output).  grid (m-blocks, 128 / kReduceRows).
 constexpr int kReduceRows = 16;
-__global__ void __launch_bounds__(kReduceRows * 8) lora_partials_reduce_kernel(const float *__restrict__ ws, float *__restrict__ out, int R, int num_n_blocks,
-                                                                                int num_tiles, int gemm_grid) {
+constexpr int kReduceThreads = 512;
+__global__ void __launch_bounds__(kReduceThreads) lora_partials_reduce_kernel(const float *__restrict__ ws, float *__restrict__ out, int R, int num_n_blocks,
+                                                                              int num_tiles, int gemm_grid) {
     ptx::griddep_launch_dependents();
     ptx::griddep_wait();   // the partials are the GEMM's output
     const int mb = blockIdx.x;
@@ -1094,19 +1097,29 @@ __global__ void __launch_bounds__(kReduceRows * 8) lora_partials_reduce_kernel(c
     const long long t_first = static_cast<long long>(mb) * num_n_blocks, t_last = t_first + num_n_blocks - 1;
     const int b_first = static_cast<int>(((t_first + 1) * gemm_grid + num_tiles - 1) / num_tiles) - 1;
     const int b_last = static_cast<int>(((t_last + 1) * gemm_grid + num_tiles - 1) / num_tiles) - 1;
-    const int r4 = R / 4;
-    for (int idx = threadIdx.x; idx < kReduceRows * r4; idx += blockDim.x) {
+    const int quarter = (b_last - b_first + 4) / 4;
+    const int part = threadIdx.x & 3;
+    const int my_first = b_first + part * quarter, my_last = min(b_last, my_first + quarter - 1);
+    const int r4 = R / 4;   // (R is a multiple of 16: the 8 (row, 4 ranks) outputs of a warp are all inside or all outside the range below)
+    for (int idx = threadIdx.x >> 2; idx < kReduceRows * r4; idx += kReduceThreads / 4) {
         const int row = blockIdx.y * kReduceRows + idx / r4, c4 = idx % r4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int b = b_first; b <= b_last; b++) {
+#pragma unroll 4
+        for (int b = my_first; b <= my_last; b++) {
             const float4 v = __ldcg(reinterpret_cast<const float4 *>(ws + (static_cast<size_t>(mb + b) * 128 + row) * R) + c4);
             acc.x += v.x;
             acc.y += v.y;
             acc.z += v.z;
             acc.w += v.w;
         }
-        *(reinterpret_cast<float4 *>(out + (static_cast<size_t>(mb) * 128 + row) * R) + c4) = acc;
+#pragma unroll
+        for (int sh = 1; sh <= 2; sh <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sh);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sh);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, sh);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, sh);
+        }
+        if (part == 0) *(reinterpret_cast<float4 *>(out + (static_cast<size_t>(mb) * 128 + row) * R) + c4) = acc;
     }
 }
 
@@ -1210,7 +1223,7 @@ int launch(const nb200_gemm_args &a, cudaStream_t stream) {
     count_launch();
     NB200_CUDA_CHECK(cudaGetLastError());
     if (p.ws_partial != nullptr) {   // the fixed-order sum of the per-CTA partial projections
-        LaunchCfg lr(dim3(a.Mp / BM, BM / kReduceRows), dim3(kReduceRows * 8), 0, stream);
+        LaunchCfg lr(dim3(a.Mp / BM, BM / kReduceRows), dim3(kReduceThreads), 0, stream);
         NB200_CUDA_CHECK(cudaLaunchKernelEx(&lr.cfg, lora_partials_reduce_kernel, static_cast<const float *>(p.ws_partial), a.lora_act_out, a.R_down, p.num_n_blocks,
                                             p.num_tiles, grid));
         count_launch();
