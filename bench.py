@@ -73,11 +73,29 @@ def gemm_bytes(M, K, N, R, fp4):
 
 
 def host_threads() -> int:
-    """threads this process may actually use (cgroup / affinity aware), not os.cpu_count()"""
+    """threads this process may actually use: the affinity mask, capped by the cgroup CPU quota when one is set (a box whose mask shows 128 CPUs
+    behind a quota of a few cores runs 128 OpenMP threads SLOWER than 8 -- r01: the same sample took 41 ms on one box and 651 ms on another)"""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = max(1, len(os.sched_getaffinity(0)))
     except AttributeError:  # pragma: no cover
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:      # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()[:2]
+            if q != "max":
+                quota = int(q) / int(per)
+    except (OSError, ValueError):
+        try:                                            # cgroup v1
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f1, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                q, per = int(f1.read()), int(f2.read())
+                if q > 0 and per > 0:
+                    quota = q / per
+        except (OSError, ValueError):
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.999)))
+    return n
 
 
 # --------------------------------------------------------------------------------------------
@@ -518,9 +536,24 @@ class CpuSample:
             from oracle import csvdq
 
             csvdq.build()
-            csvdq.set_threads(self.cores)
             self.fn = lambda: csvdq.linear_forward(self.layer, self.x)
             self.impl = "plain-C oracle (oracle/svdq_ref.c, OpenMP)"
+            # "all the host threads it can use" = the team size that is actually fastest on this box: every hyper-thread of a 2-socket host is
+            # not (3072 weight rows over 128 threads: 24 rows each, memory-bound decode on two NUMA nodes).  One warm + one timed rep per size.
+            tried = {}
+            n = self.cores
+            while n >= 1:
+                csvdq.set_threads(n)
+                self.fn()
+                t0 = time.perf_counter()
+                self.fn()
+                tried[n] = time.perf_counter() - t0
+                if n <= 8:
+                    break
+                n //= 2
+            self.cores = min(tried, key=tried.get)
+            self.tried = tried
+            csvdq.set_threads(self.cores)
         except Exception as e:  # no gcc on the box: the torch restatement
             torch.set_num_threads(min(self.cores, 32))
             self.cores = torch.get_num_threads()
@@ -537,8 +570,10 @@ class CpuSample:
         return (time.perf_counter() - t0) / reps, reps
 
     def describe(self, precision: str, dt: float, reps: int) -> str:
+        tried = getattr(self, "tried", None)
+        how = ("fastest team size of " + ", ".join(f"{n}: {t * 1e3:.0f} ms" for n, t in tried.items())) if tried else "sched_getaffinity / cgroup quota"
         return (f"1 SVDQuant linear 3072x3072 r32 M=256 ({precision}), reference-emulating arithmetic, {self.impl}, {self.cores} threads "
-                f"(sched_getaffinity): {reps} reps x {dt * 1e3:.1f} ms")
+                f"({how}): {reps} reps x {dt * 1e3:.1f} ms")
 
 
 def run_reference_arm(args):
