@@ -18,13 +18,11 @@ namespace nb200 {
 namespace {
 
 constexpr int kRopeWarps = 8;
-constexpr int kUnitHeads = 16;   // heads per warp: 4 KB of the row
 
-// One kernel for both hand-offs.  A WARP owns 16 consecutive heads of one row (kBatch steps of 4 heads); 8 lanes share a 128-wide head (16
-// consecutive columns = 32 bytes each), so one step of the warp covers 4 heads = 1 KB of the row, contiguous (r02h launch list: the first version
-// -- lanes = heads, 256-byte stride between lanes -- took 43.7 us for 4352 x 6144 against an ~18 us traffic floor; warp = whole row took 29.0 us:
-// 544 CTAs of 8 rows are 1.23 waves of the 444 resident CTAs, so the second wave ran at a quarter of the chip -- with 16-head units the grid is
-// 3.7 waves of work a third the size).  A lane keeps the 8 (sin, cos) pairs of its columns in registers for its 16 heads.  The head's sum of squares is 8 partial sums of 16 columns (sequential fp32 FMA chains) combined by a
+// One kernel for both hand-offs.  A WARP owns one row; 8 lanes share a 128-wide head (16 consecutive columns = 32 bytes each), so one step of
+// the warp covers 4 heads = 1 KB of the row, contiguous (r02h launch list: the first version -- lanes = heads, 256-byte stride between lanes --
+// took 43.7 us for 4352 x 6144 against an ~18 us traffic floor).  The row's 64 (sin, cos) pairs are read once: a lane keeps the 8 pairs of its
+// columns in registers for all heads.  The head's sum of squares is 8 partial sums of 16 columns (sequential fp32 FMA chains) combined by a
 // fixed xor tree ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)) -- the order the GEMMs' fused epilogues use as well, so all routes stay bit-identical.
 //   PACK = false: RMSNorm(Q, K) + RoPE in place on qkv [M, N]; V untouched.
 //   PACK = true : reads the plain projection [Mp, N] and writes the attention operands (EpiloguePackQKV, epilogues.cuh:427-550): fp16
@@ -42,21 +40,17 @@ __global__ void __launch_bounds__(kRopeWarps * 32) rope_kernel(hT *__restrict__ 
     __syncthreads();
     ptx::griddep_wait();   // qkv is the GEMM's output
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * kRopeWarps + warp;
+    if (m >= M) return;
     const int H = (N / 3) / 128;
     const int heads = PACK ? 3 * H : 2 * H;            // Q heads, K heads (, V heads): contiguous in the row
-    const int units_per_row = (heads + kUnitHeads - 1) / kUnitHeads;
-    const long long unit = static_cast<long long>(blockIdx.x) * kRopeWarps + warp;
-    const int m = static_cast<int>(unit / units_per_row);
-    if (m >= M) return;
-    const int h_begin = static_cast<int>(unit % units_per_row) * kUnitHeads;
-    const int h_end = min(heads, h_begin + kUnitHeads);
     const int sub = lane & 7, hq = lane >> 3;          // 16-column slice of a head, head inside the group of 4
     hT *row = qkv + static_cast<size_t>(m) * N + sub * 16;
     if constexpr (PACK) {
         if (m >= attn_tokens) {   // pad rows: the key mask is NaN, queries and values are zero
-            for (int h0 = h_begin; h0 < h_end; h0 += 4) {
+            for (int h0 = 0; h0 < heads; h0 += 4) {
                 const int head = h0 + hq;
-                if (head >= h_end) break;
+                if (head >= heads) break;
                 const int part = head / H, hh = head % H;
                 __half *dst = (part == 0 ? out_q + hh * sq : part == 1 ? out_k + hh * sk : out_v + hh * sv) + static_cast<size_t>(m) * 128 + sub * 16;
                 const uint32_t fill = part == 1 ? 0x7FFF7FFFu : 0u;
@@ -75,14 +69,13 @@ __global__ void __launch_bounds__(kRopeWarps * 32) rope_kernel(hT *__restrict__ 
         const int pr = sub * 8 + i;
         sc[i] = __ldg(reinterpret_cast<const float2 *>(rot_row + (pr >> 2) * 128 + (pr & 3) * 4));
     }
-    constexpr int kBatch = kUnitHeads / 4;   // head groups in flight: 8 x 16-byte loads per lane
-    {
-        const int h0 = h_begin;
+    constexpr int kBatch = 4;   // head groups in flight: 8 x 16-byte loads per lane
+    for (int h0 = 0; h0 < heads; h0 += 4 * kBatch) {
         uint4 v[kBatch][2];
 #pragma unroll
         for (int u = 0; u < kBatch; u++) {
             const int head = h0 + 4 * u + hq;
-            if (head < h_end) {
+            if (head < heads) {
                 v[u][0] = *reinterpret_cast<const uint4 *>(row + static_cast<size_t>(head) * 128);
                 v[u][1] = *reinterpret_cast<const uint4 *>(row + static_cast<size_t>(head) * 128 + 8);
             } else {
@@ -92,7 +85,7 @@ __global__ void __launch_bounds__(kRopeWarps * 32) rope_kernel(hT *__restrict__ 
 #pragma unroll
         for (int u = 0; u < kBatch; u++) {
             const int head = h0 + 4 * u + hq;          // (the 8 lanes of a head agree on `head`: the shuffles below stay inside the group)
-            const bool live = head < h_end;
+            const bool live = head < heads;
             const int part = live ? head / H : 0, hh = live ? head % H : 0;
             const uint32_t xw[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
             float sumsq = 0.f;
@@ -151,8 +144,7 @@ int rope_inplace_dispatch(int dtype, void *qkv, int M, int N, const void *norm_q
     NB200_REQUIRE(qkv && norm_q && norm_k && rotary, "NULL tensor");
     NB200_REQUIRE(N % 384 == 0, "N must be 3 * heads * 128");
     if (M <= 0) return NB200_OK;
-    const long long units = static_cast<long long>(M) * ((2 * (N / 384) + kUnitHeads - 1) / kUnitHeads);
-    const unsigned grid = static_cast<unsigned>((units + kRopeWarps - 1) / kRopeWarps);
+    const unsigned grid = static_cast<unsigned>((M + kRopeWarps - 1) / kRopeWarps);
     LaunchCfg lc(dim3(grid), dim3(kRopeWarps * 32), 0, stream);
     __half *none = nullptr;
     if (dtype == NB200_BF16) {
@@ -177,8 +169,7 @@ int rope_pack_dispatch(int dtype, const void *qkv, int Mp, int N, const void *no
     NB200_REQUIRE(qkv && norm_q && norm_k && rotary && out_q && out_k && out_v, "NULL tensor");
     NB200_REQUIRE(N % 384 == 0, "N must be 3 * heads * 128");
     if (Mp <= 0) return NB200_OK;
-    const long long units = static_cast<long long>(Mp) * ((3 * (N / 384) + kUnitHeads - 1) / kUnitHeads);
-    const unsigned grid = static_cast<unsigned>((units + kRopeWarps - 1) / kRopeWarps);
+    const unsigned grid = static_cast<unsigned>((Mp + kRopeWarps - 1) / kRopeWarps);
     LaunchCfg lc(dim3(grid), dim3(kRopeWarps * 32), 0, stream);
     if (dtype == NB200_BF16) {
         NB200_CUDA_CHECK(cudaLaunchKernelEx(&lc.cfg, rope_kernel<__nv_bfloat16, true>, static_cast<__nv_bfloat16 *>(const_cast<void *>(qkv)), Mp, N,
