@@ -58,6 +58,8 @@ def main():
         for k, c in kernels.items():
             name = demangled[k]
             base = name.split("<")[0]
+            if base == "gemm_w4a4_kernel":   # one line per epilogue (last template argument: 0 default, 1 fused quantise, 2 RMSNorm + RoPE, 3 LiteLA)
+                base += " epilogue " + name.rstrip(">").split(",")[-1].strip()
             score = (("__nv_bfloat16" in name), sum(c.values()))
             if base not in fam or score > fam[base][0]:
                 fam[base] = (score, k)
