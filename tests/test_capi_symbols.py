@@ -103,3 +103,34 @@ def test_glue_and_litela_entry_points_validate_arguments_without_a_gpu():
     arr = (ctypes.c_void_p * 7)(*([16] * 7))
     assert lib.nb200_split_mod(1, 16, arr, 7, 70, None) == -1            # 2..6 outputs
     assert lib.nb200_add(1, 16, 16, 16, 0, None) == 0                     # empty tensors are a no-op
+
+
+def test_litela_epilogue_arguments_are_validated_without_a_gpu():
+    """nb200_gemm_args.out_vk (EpilogueLiteLA inside the GEMM, launch_impl:311-346): the preconditions the reference asserts (numBlocksN % 3 == 0,
+    tokens a multiple of the tile height, out = relu(Q) of exactly [Mp, N/3]) come back as status -1 + message before any CUDA call."""
+    import ctypes
+
+    from nunchaku_b200._C import GemmArgs
+
+    def args(**kw):
+        g = GemmArgs()
+        g.act = g.wgt = g.ascales = g.wscales = 256          # fake, 16-byte aligned: validation never dereferences
+        g.Mp, g.N, g.K = 512, 384, 256
+        g.dtype, g.fp4 = 1, 1
+        g.out, g.M_out, g.N_out = 256, 512, 128
+        g.out_vk, g.vk_tokens = 256, 256
+        for k, v in kw.items():
+            setattr(g, k, v)
+        return g
+
+    def rejected(g, needle):
+        assert lib.nb200_gemm_w4a4(ctypes.byref(g), None) == -1
+        assert needle in lib.nb200_last_error(), lib.nb200_last_error()
+
+    rejected(args(N=256, N_out=128), b"multiple of 128")               # N / 3 not a whole number of 128-wide tiles
+    rejected(args(vk_tokens=192), b"vk_tokens")                         # a 128-row tile would straddle two images
+    rejected(args(vk_tokens=384), b"vk_tokens")                         # does not divide Mp
+    rejected(args(N_out=384), b"[Mp, N / 3]")                           # out must be relu(Q) only
+    rejected(args(out=None), b"must be non-NULL")
+    rejected(args(qout=256, oscales=256, smooth_next=256), b"out_vk goes with out")
+    rejected(args(rotary_emb=256, norm_q=256, norm_k=256), b"out_vk goes with out")
