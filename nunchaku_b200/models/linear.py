@@ -11,6 +11,8 @@ set of converted weights instead of per-call tensor plumbing:
 """
 from __future__ import annotations
 
+from dataclasses import fields as dataclass_fields
+
 import torch
 from torch import nn
 
@@ -83,6 +85,19 @@ class SVDQW4A4Linear(nn.Module):
                                                     wcscales=None if self.wcscales is None else self.wcscales.data, alpha=self.wtscale, fp4=self.fp4)
             self._b200_alpha = self.wtscale
         return self._b200
+
+    def _apply(self, fn, recurse=True):
+        """``module.to(device)`` / ``.cuda(i)`` after the conversion: the converted bundle follows the parameters to their new device (it cannot be
+        rebuilt once ``release_reference_layout()`` has dropped the checkpoint layout).  Dtype casts do not touch it (its fp32 vectors stay fp32)."""
+        out = super()._apply(fn, recurse)
+        w = self._b200
+        if w is not None and w.qweight.device != self.qweight.device:
+            dev = self.qweight.device
+            for f in dataclass_fields(w):
+                v = getattr(w, f.name)
+                if isinstance(v, torch.Tensor):
+                    setattr(w, f.name, v.to(dev))
+        return out
 
     def invalidate(self) -> None:
         """Call after changing parameters in place (LoRA merge, ``param.data.copy_``); ``load_state_dict`` does it itself."""

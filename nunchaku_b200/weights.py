@@ -46,8 +46,11 @@ class B200Weights:
         elif alpha != 1.0:
             cs = torch.full((N,), alpha, dtype=torch.float32, device=qweight.device)
         rank = 0 if proj_up is None else proj_up.shape[1]
+        hts = [t.dtype for t in (proj_up, bias, smooth, wcscales, None if fp4 else wscales) if t is not None and t.dtype in (torch.float16, torch.bfloat16)]
+        if not hts:
+            raise ValueError("cannot tell the layer's 16-bit type: pass at least one of proj_up / bias / smooth / wcscales (gemm_w4a4.cu:63-73)")
         return cls(
-            N=N, K=K, rank=rank, fp4=fp4, dtype=(proj_up if proj_up is not None else bias).dtype,
+            N=N, K=K, rank=rank, fp4=fp4, dtype=hts[0],
             qweight=repack.qweight(qweight, fp4, cache=False),
             wscales=repack.wscales(wscales, N, K, fp4, cache=False),
             bias=None if bias is None else repack.channel_vector(bias, out_f32=True, cache=False),

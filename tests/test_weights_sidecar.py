@@ -51,3 +51,24 @@ def test_fingerprint_follows_the_bytes():
     assert f0 != B200Weights.fingerprint(qweight=a2, bias=b, alpha=1.0, wcscales=None)
     assert f0 != B200Weights.fingerprint(qweight=a, bias=b, alpha=0.5, wcscales=None)
     assert f0 != B200Weights.fingerprint(qweight=a.view(8, 8), bias=b, alpha=1.0, wcscales=None)
+
+
+def test_converted_weights_follow_a_device_move():
+    """module.to(device) after the conversion moves the B200Weights bundle with the parameters (CPU stand-in: cpu -> meta); a dtype cast leaves it alone."""
+    import torch
+
+    from nunchaku_b200.models.linear import SVDQW4A4Linear
+    from nunchaku_b200.weights import B200Weights
+
+    m = SVDQW4A4Linear(128, 128, rank=16, precision="nvfp4", torch_dtype=torch.bfloat16, device="cpu")
+    z = lambda *shape, dt=torch.uint8: torch.zeros(*shape, dtype=dt)   # noqa: E731
+    m._b200 = B200Weights(N=128, K=128, rank=16, fp4=True, dtype=torch.bfloat16, qweight=z(128, 64), wscales=z(1024), bias=z(128, dt=torch.float32),
+                          cscale=None, lora_up=z(128, 32, dt=torch.bfloat16), lora_down=z(128, 16, dt=torch.bfloat16), lora_down_next=None,
+                          smooth=z(128, dt=torch.bfloat16))
+    m._b200_alpha = m.wtscale
+    m.to(torch.float16)                                    # cast: parameters change dtype, the bundle (fp32 bias included) is untouched
+    assert m._b200.bias.dtype == torch.float32 and m._b200.qweight.device.type == "cpu"
+    m.to("meta")
+    assert m.qweight.device.type == "meta"
+    assert all(getattr(m._b200, n).device.type == "meta" for n in ("qweight", "wscales", "bias", "lora_up", "lora_down", "smooth"))
+    assert m._b200.cscale is None and m._b200.lora_down_next is None
