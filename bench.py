@@ -794,7 +794,7 @@ def main() -> int:
     # dram bytes of ONE launch on the primary shape (M=4096, K=N=3072, r=32) from the committed `ncu --set full` captures (profiles/)
     traffic = {"int4": 12.5e6, "nvfp4": 13.2e6}[args.precision]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_basis": "bytes per launch, primary shape 4096x3072x3072, ncu (algorithmic: 37.6 MB incl. the 25 MB output that stays in L2)",
+                "traffic_basis": "dram bytes per launch, primary shape 4096x3072x3072, ncu --set full (profiles/r02e_gemm_nvfp4_ncu.txt, profiles/r01x_gemm_int4_ncu.txt; algorithmic: 37.6 MB incl. the 25 MB output that stays in L2)",
                 "kernel": "gemm_nvfp4_cluster_kernel" if fp4 else "gemm_w4a4_kernel", "launches": n_gemm, "avg_launch_us": g_ms * 1e3 / n_gemm,
                 "timing": "the step's 304 fused-GEMM operator calls alone (the 57 large-M QKV calls include their in-place RMSNorm+RoPE kernel), CUDA-graph replay, CUDA events on the launch stream", "peak_basis": peak_basis,
                 "gemm_share_of_step": g_ms / ms_per_step}
