@@ -301,7 +301,7 @@ gemm_nvfp4_cluster_kernel(const __grid_constant__ CUtensorMap tm_act, const __gr
                 const uint32_t sf_set = tmem_base + (kb & 1) * kSfSet;   // two scale-factor sets in TMEM (k-block parity)
                 // CTA-scope acquire on every wait of this warp: what it orders is async-proxy work (TMA writes, tcgen05 reads) and the
                 // peer's fence.proxy.async precedes its arrive, the same contract CUTLASS's ClusterBarrier::wait relies on; a satisfied
-                // cluster-scope try_wait costs ~250 clk on the issuing thread every stage (profiles/r02_issue_timeline.md); bit 8192 = old way
+                // cluster-scope try_wait costs ~250 clk on the issuing thread every stage (tools/gemm_prof.py --timeline); bit 8192 = old way
                 if (cluster_acq) mbar_wait_cluster(&s.full[st.idx], st.phase);
                 else mbar_wait(&s.full[st.idx], st.phase);
                 if (lane == 0) mark(3);

@@ -1248,7 +1248,7 @@ int launch_bn(const nb200_gemm_args &a, cudaStream_t stream) {
     // fill the chip (the 256-token text stream keeps the narrow single-CTA tiles: more CTAs busy).
     if constexpr (FP4) {
         if (a.block_n == 1024 || a.block_n == 2048) return gemm_nvfp4_cluster_dispatch(a, stream, a.block_n / 1024);
-        // measured on one box (tools/gemm_ablate.py, profiles/r02_ablation.md): one pair per cluster == the r01 pair kernel on the plain
+        // measured on one box (tools/gemm_ablate.py): one pair per cluster == the r01 pair kernel on the plain
         // epilogue and it carries the RoPE epilogue on 256-wide tiles; two pairs per cluster (A multicast) is NOT faster -- the bound
         // is what each SM has to receive, which multicast does not change -- and only 33 clusters of 4 fit on the 148 SMs
         if (a.block_n == 0 && a.N % 256 == 0 && (a.Mp / 256) * (a.N / 256) >= 64) return gemm_nvfp4_cluster_dispatch(a, stream, 1);

@@ -1,6 +1,6 @@
 // CTA-pair (cta_group::2) version of the fused SVDQuant W4A4 GEMM: the default-epilogue work horse.
 //
-// Why pairs (profiles/r01_gemm_*.txt): at full tensor rate every dense
+// Why pairs (profiles/r01x_gemm_*_ncu.txt): at full tensor rate every dense
 // tcgen05 kind reads 96 B/clk of operands from shared memory for a 128x256 tile and TMA writes
 // the same 96 B/clk -- more than the 128 B/clk one SM's shared memory delivers -- and a 222 KB
 // smem budget cannot hide L2 latency at that rate.  A pair of SMs computing a 256x256 tile splits

@@ -2,7 +2,7 @@
 //
 // Same contract as quantize.cu (reference quantize_w4a4_fuse_lora_kernel, gemm_w4a4.cuh:1097-1184).
 // v1 streamed rows straight into registers and was latency bound (16 % of HBM peak, ncu
-// profiles/r01_quantize.txt: 8 resident warps, 30 % issue active, loads serialised behind math).
+// profiles/r01a_quantize_v1_int4_ncu.txt: 8 resident warps, 30 % issue active, loads serialised behind math).
 // v2 decouples memory from math:
 //   * one elected producer thread keeps a deep ring of TMA tiles in flight per CTA
 //     (cp.async.bulk.tensor.2d, [32 rows x 64 k] = one quantisation group per row, 128B swizzle,
