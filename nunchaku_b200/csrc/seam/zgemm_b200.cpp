@@ -8,7 +8,7 @@
 // so that src/Linear.cpp, src/FluxModel.cpp, src/SanaModel.cpp and nunchaku/csrc/* compile and link UNCHANGED.
 // It is compiled against the reference's headers (Tensor.h, common.h, zgemm.h) -- see oracle/ref_build/build_ref.sh,
 // which links it with the reference's untouched src/Linear.cpp into oracle/_ref/libnunchaku_seam.so;
-// tests/test_gpu_seam.py drives GEMM_W4A4::forward / forward_quant / the fused MLP / the 10-argument QKV forward
+// tests/test_gpu_vs_reference.py drives GEMM_W4A4::forward / forward_quant / the fused MLP / the 10-argument QKV forward
 // through it and compares with the reference's own kernels on the same B200.
 //
 // Weight-side tensors arrive in the checkpoint (mma.sync fragment) layout and are converted
