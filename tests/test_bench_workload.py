@@ -43,3 +43,33 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["metric"].startswith("FLUX.1-schnell") and "workload" in d["config"]
+
+
+def test_host_threads_respects_the_cgroup_quota(monkeypatch):
+    """The CPU arm's thread count is the affinity mask capped by the cgroup CPU quota (r01: 128 OpenMP threads behind a small quota made the
+    same sample 16x slower on one box than on another)."""
+    import builtins
+    import io
+
+    real_open = builtins.open
+
+    def fake(quota_text):
+        def _open(path, *a, **k):
+            if path == "/sys/fs/cgroup/cpu.max":
+                if quota_text is None:
+                    raise OSError("no cgroup v2")
+                return io.StringIO(quota_text)
+            if str(path).startswith("/sys/fs/cgroup/cpu/"):
+                raise OSError("no cgroup v1")
+            return real_open(path, *a, **k)
+        return _open
+
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(128)), raising=False)
+    monkeypatch.setattr(builtins, "open", fake("800000 100000"))
+    assert bench.host_threads() == 8
+    monkeypatch.setattr(builtins, "open", fake("250000 100000"))
+    assert bench.host_threads() == 3          # 2.5 CPUs of quota -> 3 threads
+    monkeypatch.setattr(builtins, "open", fake("max 100000"))
+    assert bench.host_threads() == 128
+    monkeypatch.setattr(builtins, "open", fake(None))
+    assert bench.host_threads() == 128
