@@ -131,3 +131,33 @@ def test_round2_ops_reject_cpu_tensors_and_keep_reference_signatures():
         with pytest.raises(RuntimeError, match="no CPU path"):
             GraphedStep(lambda: None)
     assert inspect.signature(svdq_gemm_w4a4_cuda).parameters["qkv_scratch"].kind is inspect.Parameter.KEYWORD_ONLY
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under nunchaku_b200/ may import it (or name its libraries), and bench.py only inside its CPU /
+    reference comparison legs -- the timed GPU path (StackRunner / FullRunner / main's timed regions) stays clear of it."""
+    import ast
+    import glob
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, "nunchaku_b200", "**", "*.py"), recursive=True):
+        src = open(path).read()
+        tree = ast.parse(src)
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), f"{path} imports the oracle"
+        assert "oracle/_ref" not in src and "libsvdq_ref" not in src, path
+    for path in glob.glob(os.path.join(root, "nunchaku_b200", "csrc", "*.cu")) + glob.glob(os.path.join(root, "nunchaku_b200", "csrc", "*.cuh")):
+        assert "oracle/" not in open(path).read().replace("oracle/ref_build", ""), path   # (comments may name the build recipe of the seams)
+    # bench.py: the oracle appears only in the functions of the comparison legs
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    allowed = {"reference_gpu_leg", "CpuSample", "__init__"}
+    for fn in [n for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.ClassDef))]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                assert fn.name in allowed, f"bench.py: {fn.name} imports the oracle"
